@@ -1,0 +1,215 @@
+"""ctypes binding of include/b200vor.h (libb200vor.so).
+
+Thin by design: every method is one C-ABI call.  There is no CPU fallback: if the
+shared library is missing, or no CUDA device is present, the call raises.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libb200vor.so")
+
+BOX_ID = 0xFFFFFFF0
+CELL_OK = 0
+CELL_UNCERTIFIED = 1
+CELL_UNCERTAIN = 2
+CELL_EMPTY = 4
+CELL_BOXFACE = 8
+CELL_OVERFLOW = 16
+CELL_DUPLICATE = 32
+FCAP = 64
+
+# every symbol include/b200vor.h declares
+EXPORTS = [
+    "b200vor_version", "b200vor_last_error", "b200vor_create", "b200vor_destroy",
+    "b200vor_set_domain_box", "b200vor_set_domain_periodic", "b200vor_set_points",
+    "b200vor_knn", "b200vor_knn_points", "b200vor_compute_cells", "b200vor_get_cells",
+    "b200vor_get_faces", "b200vor_lloyd", "b200vor_get_stats",
+    "b200vor_set_points_per_cell",
+]
+
+
+class CellParams(ctypes.Structure):
+    _fields_ = [("k0", ctypes.c_uint32), ("kmax", ctypes.c_uint32),
+                ("want_faces", ctypes.c_uint32), ("mode", ctypes.c_uint32)]
+
+
+class Stats(ctypes.Structure):
+    _fields_ = [
+        ("ms_grid", ctypes.c_float), ("ms_knn", ctypes.c_float),
+        ("ms_clip", ctypes.c_float), ("ms_total", ctypes.c_float),
+        ("passes", ctypes.c_uint32),
+        ("n_pass", ctypes.c_uint32 * 8), ("k_pass", ctypes.c_uint32 * 8),
+        ("n_uncertified", ctypes.c_uint32), ("n_uncertain", ctypes.c_uint32),
+        ("n_empty", ctypes.c_uint32), ("n_boxface", ctypes.c_uint32),
+        ("n_overflow", ctypes.c_uint32), ("n_duplicate", ctypes.c_uint32),
+        ("sum_planes", ctypes.c_uint64), ("sum_tests", ctypes.c_uint64),
+        ("sum_created", ctypes.c_uint64), ("sum_tets", ctypes.c_uint64),
+        ("gpu_launches", ctypes.c_uint64),
+        ("grid_dim", ctypes.c_uint32 * 3), ("reserved", ctypes.c_uint32),
+    ]
+
+    def as_dict(self):
+        d = {}
+        for name, _ in self._fields_:
+            v = getattr(self, name)
+            d[name] = list(v) if hasattr(v, "__len__") else v
+        return d
+
+
+class B200VorError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library():
+    """Loads libb200vor.so (raises if it was not built: there is no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise B200VorError(
+            "%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C geogram_b200/csrc` (there is no CPU fallback)" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, u32, dbl, i32 = ctypes.c_void_p, ctypes.c_uint32, ctypes.c_double, ctypes.c_int
+    lib.b200vor_last_error.restype = ctypes.c_char_p
+    lib.b200vor_create.argtypes = [ctypes.POINTER(vp), i32]
+    lib.b200vor_destroy.argtypes = [vp]
+    lib.b200vor_destroy.restype = None
+    lib.b200vor_set_domain_box.argtypes = [vp, vp]
+    lib.b200vor_set_domain_periodic.argtypes = [vp, dbl]
+    lib.b200vor_set_points.argtypes = [vp, u32, vp, u32, vp, i32]
+    lib.b200vor_knn.argtypes = [vp, u32, vp, vp, i32]
+    lib.b200vor_knn_points.argtypes = [vp, u32, vp, u32, vp, vp, i32]
+    lib.b200vor_compute_cells.argtypes = [vp, ctypes.POINTER(CellParams)]
+    lib.b200vor_get_cells.argtypes = [vp, vp, vp, vp, i32]
+    lib.b200vor_get_faces.argtypes = [vp, vp, vp, vp, u32, i32]
+    lib.b200vor_lloyd.argtypes = [vp, u32, ctypes.POINTER(CellParams), vp, i32]
+    lib.b200vor_get_stats.argtypes = [vp, ctypes.POINTER(Stats)]
+    lib.b200vor_set_points_per_cell.argtypes = [vp, dbl]
+    _lib = lib
+    return lib
+
+
+def _ptr(a):
+    """Host numpy array / raw device address (int) / None -> void*"""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return ctypes.c_void_p(a)
+    assert a.flags["C_CONTIGUOUS"]
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+class Context(object):
+    """One engine instance on one GPU (owns its stream and device buffers)."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        h = ctypes.c_void_p()
+        self._check(self.lib.b200vor_create(ctypes.byref(h), int(device)))
+        self.h = h
+        self.n = 0
+
+    def _check(self, rc):
+        if rc != 0:
+            raise B200VorError("b200vor error %d: %s" % (
+                rc, self.lib.b200vor_last_error().decode("utf-8", "replace")))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.b200vor_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- domain / points ----
+    def set_domain_box(self, box):
+        box = np.ascontiguousarray(box, np.float64)
+        self._check(self.lib.b200vor_set_domain_box(self.h, _ptr(box)))
+
+    def set_domain_periodic(self, period=1.0):
+        self._check(self.lib.b200vor_set_domain_periodic(self.h, float(period)))
+
+    def set_points_per_cell(self, ppc):
+        self._check(self.lib.b200vor_set_points_per_cell(self.h, float(ppc)))
+
+    def set_points(self, xyz, w=None):
+        """Host numpy arrays (copied H2D inside the call)."""
+        xyz = np.ascontiguousarray(xyz, np.float64)
+        if w is not None:
+            w = np.ascontiguousarray(w, np.float64)
+        self.n = xyz.shape[0]
+        self._check(self.lib.b200vor_set_points(self.h, self.n, _ptr(xyz), 3, _ptr(w), 0))
+
+    def set_points_device(self, n, xyz_ptr, w_ptr=None, stride=3):
+        """Raw device addresses (e.g. torch.Tensor.data_ptr())."""
+        self.n = int(n)
+        self._check(self.lib.b200vor_set_points(
+            self.h, self.n, _ptr(int(xyz_ptr)), int(stride),
+            _ptr(int(w_ptr)) if w_ptr else None, 1))
+
+    # ---- kNN ----
+    def knn(self, k, want_d2=True):
+        nbr = np.zeros((self.n, k), np.uint32)
+        d2 = np.zeros((self.n, k)) if want_d2 else None
+        self._check(self.lib.b200vor_knn(self.h, int(k), _ptr(nbr), _ptr(d2), 0))
+        return nbr, d2
+
+    def knn_points(self, q, k):
+        q = np.ascontiguousarray(q, np.float64)
+        nq = q.shape[0]
+        nbr = np.zeros((nq, k), np.uint32)
+        d2 = np.zeros((nq, k))
+        self._check(self.lib.b200vor_knn_points(self.h, nq, _ptr(q), int(k), _ptr(nbr), _ptr(d2), 0))
+        return nbr, d2
+
+    # ---- cells ----
+    def compute_cells(self, k0=0, kmax=0, want_faces=False, mode=0):
+        p = CellParams(int(k0), int(kmax), 1 if want_faces else 0, int(mode))
+        self._check(self.lib.b200vor_compute_cells(self.h, ctypes.byref(p)))
+
+    def get_cells(self):
+        m = np.zeros(self.n)
+        mg = np.zeros((self.n, 3))
+        status = np.zeros(self.n, np.uint8)
+        self._check(self.lib.b200vor_get_cells(self.h, _ptr(m), _ptr(mg), _ptr(status), 0))
+        return m, mg, status
+
+    def get_cells_device(self, m_ptr, mg_ptr, status_ptr):
+        self._check(self.lib.b200vor_get_cells(
+            self.h, _ptr(int(m_ptr)) if m_ptr else None, _ptr(int(mg_ptr)) if mg_ptr else None,
+            _ptr(int(status_ptr)) if status_ptr else None, 1))
+
+    def get_faces(self):
+        nf = np.zeros(self.n, np.uint32)
+        nbr = np.zeros((self.n, FCAP), np.uint32)
+        area = np.zeros((self.n, FCAP))
+        self._check(self.lib.b200vor_get_faces(self.h, _ptr(nf), _ptr(nbr), _ptr(area), FCAP, 0))
+        return nf, nbr, area
+
+    def lloyd(self, iters, k0=0, kmax=0, mode=0, want_xyz=True):
+        p = CellParams(int(k0), int(kmax), 0, int(mode))
+        out = np.zeros((self.n, 3)) if want_xyz else None
+        self._check(self.lib.b200vor_lloyd(self.h, int(iters), ctypes.byref(p), _ptr(out), 0))
+        return out
+
+    def lloyd_device(self, iters, xyz_out_ptr=None, k0=0, kmax=0, mode=0):
+        p = CellParams(int(k0), int(kmax), 0, int(mode))
+        self._check(self.lib.b200vor_lloyd(
+            self.h, int(iters), ctypes.byref(p),
+            _ptr(int(xyz_out_ptr)) if xyz_out_ptr else None, 1))
+
+    def stats(self):
+        s = Stats()
+        self._check(self.lib.b200vor_get_stats(self.h, ctypes.byref(s)))
+        return s.as_dict()

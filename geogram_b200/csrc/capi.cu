@@ -1,0 +1,555 @@
+// capi.cu -- the C ABI of include/b200vor.h: context, buffers, pass orchestration.
+#include "common.cuh"
+
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+#include <vector>
+
+namespace b200vor {
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+namespace {
+
+__global__ void max_kernel(const double* __restrict__ w, uint32_t n, double* out) {
+    __shared__ double sm[8];
+    double mx = -1e300;
+    for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        mx = fmax(mx, w[i]);
+    }
+    for(int o = 16; o > 0; o >>= 1) {
+        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if((threadIdx.x & 31) == 0) {
+        sm[threadIdx.x >> 5] = mx;
+    }
+    __syncthreads();
+    if(threadIdx.x == 0) {
+        for(int k = 1; k < 8; ++k) {
+            mx = fmax(mx, sm[k]);
+        }
+        out[blockIdx.x] = mx;
+    }
+}
+
+__global__ void gather3_kernel(const double* __restrict__ src, uint32_t stride, uint32_t n,
+                               double* __restrict__ dst) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i < n) {
+        dst[3 * size_t(i)] = src[size_t(i) * stride];
+        dst[3 * size_t(i) + 1] = src[size_t(i) * stride + 1];
+        dst[3 * size_t(i) + 2] = src[size_t(i) * stride + 2];
+    }
+}
+
+struct Timer {
+    // device-side timing of a sequence of launches on the context's stream
+    std::vector<cudaEvent_t> ev;
+    std::vector<int> kind;
+    cudaStream_t st;
+    explicit Timer(cudaStream_t s) : st(s) {}
+    ~Timer() {
+        for(cudaEvent_t e : ev) {
+            cudaEventDestroy(e);
+        }
+    }
+    void mark(int k) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        ev.push_back(e);
+        kind.push_back(k);
+    }
+    // sums the intervals that START with a mark of kind k
+    float sum(int k) {
+        float total = 0.f;
+        for(size_t i = 0; i + 1 < ev.size(); ++i) {
+            if(kind[i] == k) {
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+                total += ms;
+            }
+        }
+        return total;
+    }
+};
+
+int copy_in(void* dst, const void* src, size_t bytes, int on_device, cudaStream_t st) {
+    B200_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes,
+                                    on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+    return B200VOR_OK;
+}
+
+int copy_out(void* dst, const void* src, size_t bytes, int on_device, cudaStream_t st) {
+    B200_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes,
+                                    on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+    return B200VOR_OK;
+}
+
+int cells_pipeline(Ctx* c, const b200vor_cell_params* params, bool collect_events) {
+    b200vor_cell_params p = {48, 384, 0, 0};
+    if(params) {
+        p = *params;
+    }
+    if(p.k0 == 0) {
+        p.k0 = 48;
+    }
+    if(p.kmax == 0) {
+        p.kmax = 384;
+    }
+    if(p.kmax > 570) {
+        p.kmax = 570;
+    }
+    if(c->n == 0) {
+        set_error("b200vor_compute_cells: no points");
+        return B200VOR_ERR_ARG;
+    }
+    const uint32_t n = c->n;
+    const uint64_t ntotal = c->periodic ? 27ull * n : n;
+    // row length: k neighbours + the seed itself at rank 0
+    auto row_len = [&](uint32_t k) { return uint32_t(std::min<uint64_t>(uint64_t(k) + 1, ntotal)); };
+    int rc;
+    if((rc = c->m.reserve(n)) || (rc = c->mg.reserve(3 * size_t(n))) ||
+       (rc = c->status.reserve(n))) {
+        return rc;
+    }
+    if(p.want_faces) {
+        c->fcap = 64;
+        if((rc = c->nfaces.reserve(n)) || (rc = c->face_nbr.reserve(size_t(n) * c->fcap)) ||
+           (rc = c->face_area.reserve(size_t(n) * c->fcap))) {
+            return rc;
+        }
+    }
+    if(collect_events) {
+        if((rc = c->evcount.reserve(2 * size_t(n)))) {
+            return rc;
+        }
+    }
+    Timer T(c->stream);
+    uint32_t k = std::min(p.k0, p.kmax);
+    uint32_t nq = n;
+    const uint32_t* qlist = nullptr;
+    c->stats.passes = 0;
+    memset(c->stats.n_pass, 0, sizeof(c->stats.n_pass));
+    memset(c->stats.k_pass, 0, sizeof(c->stats.k_pass));
+    for(int pass = 0; pass < 8 && nq > 0; ++pass) {
+        uint32_t rl = row_len(k);
+        if((rc = c->knn.reserve(size_t(nq) * rl)) || (rc = c->knn_flag.reserve(nq))) {
+            return rc;
+        }
+        T.mark(1);
+        KnnJob kj = {nq, qlist, nullptr, rl, c->knn.p, nullptr, c->knn_flag.p, 0};
+        if((rc = run_knn(c, kj))) {
+            return rc;
+        }
+        T.mark(2);
+        CellJob cj = {nq, qlist, rl, c->knn.p, c->knn_flag.p, int(p.want_faces),
+                      collect_events ? 1 : 0, int(p.mode)};
+        if((rc = run_cells(c, cj))) {
+            return rc;
+        }
+        T.mark(0);
+        c->stats.n_pass[pass] = nq;
+        c->stats.k_pass[pass] = k;
+        c->stats.passes = pass + 1;
+        if(uint64_t(rl) >= ntotal || k >= p.kmax) {
+            break;
+        }
+        // re-launch only the cells that did not reach their security radius
+        if((rc = c->qlist.reserve(nq)) || (rc = c->qlist2.reserve(nq))) {
+            return rc;
+        }
+        uint32_t* out = (qlist == c->qlist.p) ? c->qlist2.p : c->qlist.p;
+        uint32_t nfail = 0;
+        if((rc = compact_failed(c, qlist, nq, out, &nfail, B200VOR_CELL_UNCERTIFIED))) {
+            return rc;
+        }
+        qlist = out;
+        nq = nfail;
+        k = std::min(2 * k, p.kmax);
+    }
+    T.mark(0);
+    B200_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    c->stats.ms_knn += T.sum(1);
+    c->stats.ms_clip += T.sum(2);
+    c->cells_valid = true;
+    c->faces_valid = p.want_faces != 0;
+    return B200VOR_OK;
+}
+
+int ensure_grid(Ctx* c) {
+    Timer T(c->stream);
+    T.mark(1);
+    int rc = build_grid(c);
+    if(rc) {
+        return rc;
+    }
+    T.mark(0);
+    B200_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    c->stats.ms_grid += T.sum(1);
+    return B200VOR_OK;
+}
+
+}  // namespace
+}  // namespace b200vor
+
+using namespace b200vor;
+
+struct b200vor_ctx {
+    Ctx c;
+};
+
+extern "C" {
+
+int b200vor_version(void) { return B200VOR_VERSION; }
+
+const char* b200vor_last_error(void) { return g_error; }
+
+int b200vor_create(b200vor_ctx** out, int device) {
+    if(!out) {
+        set_error("b200vor_create: null output pointer");
+        return B200VOR_ERR_ARG;
+    }
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if(e != cudaSuccess || count == 0) {
+        set_error("b200vor_create: no CUDA device (%s); this library has no CPU fallback",
+                  e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        return B200VOR_ERR_CUDA;
+    }
+    if(device < 0 || device >= count) {
+        set_error("b200vor_create: device %d out of range (0..%d)", device, count - 1);
+        return B200VOR_ERR_ARG;
+    }
+    B200_CUDA_CHECK(cudaSetDevice(device));
+    b200vor_ctx* h = new b200vor_ctx();
+    h->c.device = device;
+    B200_CUDA_CHECK(cudaStreamCreateWithFlags(&h->c.stream, cudaStreamNonBlocking));
+    *out = h;
+    return B200VOR_OK;
+}
+
+void b200vor_destroy(b200vor_ctx* h) {
+    if(!h) {
+        return;
+    }
+    Ctx& c = h->c;
+    cudaSetDevice(c.device);
+    cudaStreamSynchronize(c.stream);
+    c.xyz.release(); c.wgt.release(); c.cellid.release(); c.rank.release();
+    c.cell_start.release(); c.perm.release(); c.scan_tmp.release(); c.sorted.release();
+    c.knn.release(); c.knn_flag.release(); c.qlist.release(); c.qlist2.release();
+    c.counter.release(); c.m.release(); c.mg.release(); c.status.release();
+    c.nfaces.release(); c.face_nbr.release(); c.face_area.release(); c.evcount.release();
+    c.sums.release(); c.out_nbr.release(); c.out_d2.release(); c.qpts.release();
+    cudaStreamDestroy(c.stream);
+    delete h;
+}
+
+int b200vor_set_domain_box(b200vor_ctx* h, const double* box) {
+    if(!h || !box) {
+        set_error("b200vor_set_domain_box: null argument");
+        return B200VOR_ERR_ARG;
+    }
+    for(int a = 0; a < 3; ++a) {
+        if(!(box[3 + a] > box[a])) {
+            set_error("b200vor_set_domain_box: empty box");
+            return B200VOR_ERR_ARG;
+        }
+    }
+    memcpy(h->c.box, box, 6 * sizeof(double));
+    h->c.periodic = 0;
+    h->c.cells_valid = h->c.faces_valid = false;
+    return B200VOR_OK;
+}
+
+int b200vor_set_domain_periodic(b200vor_ctx* h, double period) {
+    if(!h || !(period > 0.0)) {
+        set_error("b200vor_set_domain_periodic: invalid argument");
+        return B200VOR_ERR_ARG;
+    }
+    h->c.periodic = 1;
+    h->c.period = period;
+    h->c.cells_valid = h->c.faces_valid = false;
+    return B200VOR_OK;
+}
+
+int b200vor_set_points_per_cell(b200vor_ctx* h, double ppc) {
+    if(!h || !(ppc > 0.01)) {
+        set_error("b200vor_set_points_per_cell: invalid argument");
+        return B200VOR_ERR_ARG;
+    }
+    h->c.ppc = ppc;
+    return B200VOR_OK;
+}
+
+int b200vor_set_points(b200vor_ctx* h, uint32_t n, const double* xyz, uint32_t stride,
+                       const double* w, int on_device) {
+    if(!h || !xyz || n == 0 || stride < 3) {
+        set_error("b200vor_set_points: invalid argument (n=%u stride=%u)", n, stride);
+        return B200VOR_ERR_ARG;
+    }
+    if(uint64_t(n) * 27ull >= 0xFFFFFFF0ull && h->c.periodic) {
+        set_error("b200vor_set_points: n too large for 32-bit periodic ids");
+        return B200VOR_ERR_ARG;
+    }
+    Ctx* c = &h->c;
+    B200_CUDA_CHECK(cudaSetDevice(c->device));
+    int rc;
+    if((rc = c->xyz.reserve(3 * size_t(n)))) {
+        return rc;
+    }
+    c->n = n;
+    c->cells_valid = c->faces_valid = false;
+    if(stride == 3) {
+        if((rc = copy_in(c->xyz.p, xyz, 3 * size_t(n) * sizeof(double), on_device, c->stream))) {
+            return rc;
+        }
+    } else if(on_device) {
+        gather3_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(xyz, stride, n, c->xyz.p);
+        c->stats.gpu_launches++;
+    } else {
+        B200_CUDA_CHECK(cudaMemcpy2DAsync(c->xyz.p, 3 * sizeof(double), xyz,
+                                          stride * sizeof(double), 3 * sizeof(double), n,
+                                          cudaMemcpyHostToDevice, c->stream));
+    }
+    c->has_w = (w != nullptr);
+    c->wmax = 0.0;
+    if(w) {
+        if((rc = c->wgt.reserve(n)) ||
+           (rc = copy_in(c->wgt.p, w, size_t(n) * sizeof(double), on_device, c->stream))) {
+            return rc;
+        }
+        const int nb = 128;
+        if((rc = c->sums.reserve(256))) {
+            return rc;
+        }
+        double* part = reinterpret_cast<double*>(c->sums.p);
+        max_kernel<<<nb, 256, 0, c->stream>>>(c->wgt.p, n, part);
+        c->stats.gpu_launches++;
+        double hmax[nb];
+        B200_CUDA_CHECK(cudaMemcpyAsync(hmax, part, sizeof(hmax), cudaMemcpyDeviceToHost, c->stream));
+        B200_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        c->wmax = hmax[0];
+        for(int b = 1; b < nb; ++b) {
+            c->wmax = fmax(c->wmax, hmax[b]);
+        }
+    }
+    c->stats.ms_grid = c->stats.ms_knn = c->stats.ms_clip = 0.f;
+    return ensure_grid(c);
+}
+
+int b200vor_knn(b200vor_ctx* h, uint32_t k, uint32_t* nbr, double* d2, int on_device) {
+    if(!h || !nbr || k == 0) {
+        set_error("b200vor_knn: invalid argument");
+        return B200VOR_ERR_ARG;
+    }
+    Ctx* c = &h->c;
+    if(c->n == 0 || k > c->n) {
+        set_error("b200vor_knn: k=%u exceeds the number of points (%u)", k, c->n);
+        return B200VOR_ERR_ARG;
+    }
+    B200_CUDA_CHECK(cudaSetDevice(c->device));
+    int rc;
+    uint32_t* dn = nbr;
+    double* dd = d2;
+    size_t cnt = size_t(c->n) * k;
+    if(!on_device) {
+        if((rc = c->out_nbr.reserve(cnt)) || (d2 && (rc = c->out_d2.reserve(cnt)))) {
+            return rc;
+        }
+        dn = c->out_nbr.p;
+        dd = d2 ? c->out_d2.p : nullptr;
+    }
+    // the public kNN ignores the periodic domain, like the reference's kd-tree
+    int saved = c->grid.periodic;
+    if(saved) {
+        set_error("b200vor_knn: not available on a periodic domain");
+        return B200VOR_ERR_ARG;
+    }
+    Timer T(c->stream);
+    T.mark(1);
+    KnnJob kj = {c->n, nullptr, nullptr, k, dn, dd, nullptr, 1};
+    if((rc = run_knn(c, kj))) {
+        return rc;
+    }
+    T.mark(0);
+    if(!on_device) {
+        if((rc = copy_out(nbr, dn, cnt * sizeof(uint32_t), 0, c->stream)) ||
+           (d2 && (rc = copy_out(d2, dd, cnt * sizeof(double), 0, c->stream)))) {
+            return rc;
+        }
+    }
+    B200_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    c->stats.ms_knn = T.sum(1);
+    return B200VOR_OK;
+}
+
+int b200vor_knn_points(b200vor_ctx* h, uint32_t nq, const double* q, uint32_t k,
+                       uint32_t* nbr, double* d2, int on_device) {
+    if(!h || !nbr || !q || k == 0 || nq == 0) {
+        set_error("b200vor_knn_points: invalid argument");
+        return B200VOR_ERR_ARG;
+    }
+    Ctx* c = &h->c;
+    if(c->n == 0 || k > c->n) {
+        set_error("b200vor_knn_points: k=%u exceeds the number of points (%u)", k, c->n);
+        return B200VOR_ERR_ARG;
+    }
+    if(c->grid.periodic) {
+        set_error("b200vor_knn_points: not available on a periodic domain");
+        return B200VOR_ERR_ARG;
+    }
+    B200_CUDA_CHECK(cudaSetDevice(c->device));
+    int rc;
+    uint32_t* dn = nbr;
+    double* dd = d2;
+    const double* dq = q;
+    size_t cnt = size_t(nq) * k;
+    if(!on_device) {
+        if((rc = c->out_nbr.reserve(cnt)) || (d2 && (rc = c->out_d2.reserve(cnt))) ||
+           (rc = c->qpts.reserve(3 * size_t(nq))) ||
+           (rc = copy_in(c->qpts.p, q, 3 * size_t(nq) * sizeof(double), 0, c->stream))) {
+            return rc;
+        }
+        dn = c->out_nbr.p;
+        dd = d2 ? c->out_d2.p : nullptr;
+        dq = c->qpts.p;
+    }
+    KnnJob kj = {nq, nullptr, dq, k, dn, dd, nullptr, 1};
+    if((rc = run_knn(c, kj))) {
+        return rc;
+    }
+    if(!on_device) {
+        if((rc = copy_out(nbr, dn, cnt * sizeof(uint32_t), 0, c->stream)) ||
+           (d2 && (rc = copy_out(d2, dd, cnt * sizeof(double), 0, c->stream)))) {
+            return rc;
+        }
+    }
+    B200_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return B200VOR_OK;
+}
+
+int b200vor_compute_cells(b200vor_ctx* h, const b200vor_cell_params* params) {
+    if(!h) {
+        set_error("b200vor_compute_cells: null context");
+        return B200VOR_ERR_ARG;
+    }
+    Ctx* c = &h->c;
+    B200_CUDA_CHECK(cudaSetDevice(c->device));
+    if(c->grid.periodic != c->periodic || (c->periodic && c->grid.period != c->period)) {
+        int rc = ensure_grid(c);   // the domain changed after set_points
+        if(rc) {
+            return rc;
+        }
+    }
+    c->stats.ms_knn = c->stats.ms_clip = 0.f;
+    int rc = cells_pipeline(c, params, true);
+    if(rc) {
+        return rc;
+    }
+    c->stats.ms_total = c->stats.ms_grid + c->stats.ms_knn + c->stats.ms_clip;
+    return reduce_events(c);
+}
+
+int b200vor_get_cells(b200vor_ctx* h, double* m, double* mg, uint8_t* status, int on_device) {
+    if(!h || !h->c.cells_valid) {
+        set_error("b200vor_get_cells: no cells computed");
+        return B200VOR_ERR_ARG;
+    }
+    Ctx* c = &h->c;
+    B200_CUDA_CHECK(cudaSetDevice(c->device));
+    int rc;
+    if((m && (rc = copy_out(m, c->m.p, size_t(c->n) * sizeof(double), on_device, c->stream))) ||
+       (mg && (rc = copy_out(mg, c->mg.p, 3 * size_t(c->n) * sizeof(double), on_device, c->stream))) ||
+       (status && (rc = copy_out(status, c->status.p, size_t(c->n), on_device, c->stream)))) {
+        return rc;
+    }
+    B200_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return B200VOR_OK;
+}
+
+int b200vor_get_faces(b200vor_ctx* h, uint32_t* nfaces, uint32_t* face_nbr, double* face_area,
+                      uint32_t fcap, int on_device) {
+    if(!h || !h->c.faces_valid) {
+        set_error("b200vor_get_faces: cells were not computed with want_faces=1");
+        return B200VOR_ERR_ARG;
+    }
+    Ctx* c = &h->c;
+    if(fcap != c->fcap) {
+        set_error("b200vor_get_faces: fcap must be %u", c->fcap);
+        return B200VOR_ERR_ARG;
+    }
+    B200_CUDA_CHECK(cudaSetDevice(c->device));
+    int rc;
+    size_t cnt = size_t(c->n) * fcap;
+    if((nfaces && (rc = copy_out(nfaces, c->nfaces.p, size_t(c->n) * sizeof(uint32_t), on_device, c->stream))) ||
+       (face_nbr && (rc = copy_out(face_nbr, c->face_nbr.p, cnt * sizeof(uint32_t), on_device, c->stream))) ||
+       (face_area && (rc = copy_out(face_area, c->face_area.p, cnt * sizeof(double), on_device, c->stream)))) {
+        return rc;
+    }
+    B200_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return B200VOR_OK;
+}
+
+int b200vor_lloyd(b200vor_ctx* h, uint32_t iters, const b200vor_cell_params* params,
+                  double* xyz_out, int on_device) {
+    if(!h || h->c.n == 0) {
+        set_error("b200vor_lloyd: no points");
+        return B200VOR_ERR_ARG;
+    }
+    Ctx* c = &h->c;
+    B200_CUDA_CHECK(cudaSetDevice(c->device));
+    b200vor_cell_params p = {48, 384, 0, 0};
+    if(params) {
+        p = *params;
+    }
+    p.want_faces = 0;
+    int rc;
+    c->stats.ms_knn = c->stats.ms_clip = 0.f;
+    for(uint32_t it = 0; it < iters; ++it) {
+        if(it > 0) {
+            if((rc = ensure_grid(c))) {
+                return rc;
+            }
+        }
+        if((rc = cells_pipeline(c, &p, false)) || (rc = lloyd_update(c))) {
+            return rc;
+        }
+    }
+    if(iters > 0) {
+        // keep the context consistent with the relaxed points
+        if((rc = ensure_grid(c))) {
+            return rc;
+        }
+        c->cells_valid = c->faces_valid = false;
+    }
+    if(xyz_out) {
+        if((rc = copy_out(xyz_out, c->xyz.p, 3 * size_t(c->n) * sizeof(double), on_device, c->stream))) {
+            return rc;
+        }
+    }
+    B200_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    c->stats.ms_total = c->stats.ms_grid + c->stats.ms_knn + c->stats.ms_clip;
+    return B200VOR_OK;
+}
+
+int b200vor_get_stats(b200vor_ctx* h, b200vor_stats* stats) {
+    if(!h || !stats) {
+        set_error("b200vor_get_stats: null argument");
+        return B200VOR_ERR_ARG;
+    }
+    *stats = h->c.stats;
+    return B200VOR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,170 @@
+// common.cuh -- shared declarations of the B200 Voronoi engine (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/b200vor.h"
+
+namespace b200vor {
+
+void set_error(const char* fmt, ...);
+
+#define B200_CUDA_CHECK(expr)                                                       \
+    do {                                                                            \
+        cudaError_t err__ = (expr);                                                 \
+        if(err__ != cudaSuccess) {                                                  \
+            b200vor::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr,        \
+                               cudaGetErrorString(err__));                          \
+            return B200VOR_ERR_CUDA;                                                \
+        }                                                                           \
+    } while(0)
+
+// Uniform grid over the domain.  Cell id = ix + gx*(iy + gy*iz): x is the fastest
+// axis, so a run of cells along x is one contiguous span of the sorted point array.
+struct GridDesc {
+    double lo[3];
+    double w[3];       // cell width
+    double inv_w[3];
+    int g[3];
+    int periodic;
+    double period;
+    uint32_t ncell;
+};
+
+// One seed in grid order: 32 bytes, read with two 16-byte loads.
+struct __align__(16) Seed {
+    double x, y, z, w;
+};
+
+__host__ __device__ inline int clampi(int v, int lo, int hi) {
+    return v < lo ? lo : (v > hi ? hi : v);
+}
+
+__device__ inline void cell_coords(const GridDesc& G, double x, double y, double z,
+                                   int& ix, int& iy, int& iz) {
+    ix = clampi(int(floor((x - G.lo[0]) * G.inv_w[0])), 0, G.g[0] - 1);
+    iy = clampi(int(floor((y - G.lo[1]) * G.inv_w[1])), 0, G.g[1] - 1);
+    iz = clampi(int(floor((z - G.lo[2]) * G.inv_w[2])), 0, G.g[2] - 1);
+}
+
+__device__ inline Seed load_seed(const Seed* p) {
+    const double2* q = reinterpret_cast<const double2*>(p);
+    double2 a = __ldg(q), b = __ldg(q + 1);
+    Seed s;
+    s.x = a.x; s.y = a.y; s.z = b.x; s.w = b.y;
+    return s;
+}
+
+// delaunay/periodic.h:104-113 + periodic.cpp:80-84: instance of a translation
+__host__ __device__ inline uint32_t translation_to_instance(int tx, int ty, int tz) {
+    int i = (tz + 1) + 3 * (ty + 1) + 9 * (tx + 1);
+    // reorder_instances: 13 -> 0, 0..12 -> 1..13, 14..26 unchanged
+    return uint32_t(i == 13 ? 0 : (i < 13 ? i + 1 : i));
+}
+
+// ---------------------------------------------------------------------------------
+// Context
+// ---------------------------------------------------------------------------------
+template <class T> struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;   // elements
+    int reserve(size_t n) {
+        if(n <= cap) {
+            return B200VOR_OK;
+        }
+        if(p) {
+            cudaFree(p);
+            p = nullptr;
+            cap = 0;
+        }
+        size_t want = n + n / 16 + 64;
+        B200_CUDA_CHECK(cudaMalloc(&p, want * sizeof(T)));
+        cap = want;
+        return B200VOR_OK;
+    }
+    void release() {
+        if(p) {
+            cudaFree(p);
+        }
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct Ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[8] = {};
+
+    int periodic = 0;
+    double period = 1.0;
+    double box[6] = {0, 0, 0, 1, 1, 1};
+    double ppc = 4.0;
+
+    uint32_t n = 0;
+    bool has_w = false;
+    double wmax = 0.0;
+    DevBuf<double> xyz;        // user order, packed 3n
+    DevBuf<double> wgt;        // user order
+    GridDesc grid;
+    DevBuf<uint32_t> cellid, rank, cell_start, perm, scan_tmp;
+    DevBuf<Seed> sorted;
+
+    // kNN table of the cell pipeline (rows in pass order, ids in grid order + n*instance)
+    DevBuf<uint32_t> knn;
+    DevBuf<uint8_t> knn_flag;
+    DevBuf<uint32_t> qlist, qlist2, counter;
+
+    // cell outputs, user order
+    DevBuf<double> m, mg;
+    DevBuf<uint8_t> status;
+    DevBuf<uint32_t> nfaces, face_nbr;
+    DevBuf<double> face_area;
+    uint32_t fcap = 0;
+    bool cells_valid = false, faces_valid = false;
+    DevBuf<uint32_t> evcount;        // per-cell event counts (2 words)
+    DevBuf<unsigned long long> sums; // reductions
+
+    // scratch for user-facing kNN
+    DevBuf<uint32_t> out_nbr;
+    DevBuf<double> out_d2;
+    DevBuf<double> qpts;
+
+    b200vor_stats stats = {};
+};
+
+// grid.cu
+int build_grid(Ctx* c);
+// knn.cu
+struct KnnJob {
+    uint32_t nq;
+    const uint32_t* qlist;   // grid-order indices of the queries, or NULL (= 0..nq-1)
+    const double* qpts;      // arbitrary query points (3 doubles), or NULL (= by index)
+    uint32_t k;
+    uint32_t* out_nbr;
+    double* out_d2;          // may be NULL
+    uint8_t* out_flag;       // may be NULL; 1 = row not guaranteed complete
+    int user_ids;            // 1: ids and row order in user space; 0: grid order (+n*instance)
+};
+int run_knn(Ctx* c, const KnnJob& job);
+// cell.cu
+struct CellJob {
+    uint32_t nq;
+    const uint32_t* qlist;   // grid-order indices, or NULL
+    uint32_t k;              // row length of the kNN table
+    const uint32_t* knn;
+    const uint8_t* knn_flag;
+    int want_faces;
+    int collect_events;
+    int mode;
+};
+int run_cells(Ctx* c, const CellJob& job);
+int compact_failed(Ctx* c, const uint32_t* qlist_in, uint32_t nq_in, uint32_t* qlist_out,
+                   uint32_t* count_out_host, uint8_t mask);
+int lloyd_update(Ctx* c);
+int reduce_events(Ctx* c);
+
+}  // namespace b200vor

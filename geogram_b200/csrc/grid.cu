@@ -1,0 +1,291 @@
+// grid.cu -- uniform-grid build by counting sort (replaces BalancedKdTree::build_tree,
+// points/kd_tree.cpp:429-517, as the search structure of the kNN / cell kernels).
+//
+// Three streaming passes, all HBM-bound:
+//   bin_count   read xyz (24 B/seed), write cell id + rank (8 B), atomics on the
+//               per-cell counters (L2 resident: ncell*4 B)
+//   scan        exclusive prefix sum of the counters -> cell_start
+//   bin_scatter read xyz + w + cellid + rank (40 B), write Seed (32 B) + perm (4 B)
+// Algorithmic bytes per seed: 24 read + 24(+8 padding) + 4 written.
+#include "common.cuh"
+
+#include <math.h>
+#include <stdarg.h>
+
+namespace b200vor {
+
+namespace {
+
+constexpr int kThreads = 256;
+
+__global__ void bbox_kernel(const double* __restrict__ xyz, uint32_t n, double* out) {
+    // out[0..2] = min, out[3..5] = max ; one block-level partial per block
+    __shared__ double smin[3][kThreads / 32], smax[3][kThreads / 32];
+    double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
+    for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n;
+        i += gridDim.x * blockDim.x) {
+        for(int c = 0; c < 3; ++c) {
+            double v = xyz[3 * size_t(i) + c];
+            mn[c] = fmin(mn[c], v);
+            mx[c] = fmax(mx[c], v);
+        }
+    }
+    for(int c = 0; c < 3; ++c) {
+        for(int o = 16; o > 0; o >>= 1) {
+            mn[c] = fmin(mn[c], __shfl_xor_sync(0xffffffffu, mn[c], o));
+            mx[c] = fmax(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], o));
+        }
+        if((threadIdx.x & 31) == 0) {
+            smin[c][threadIdx.x >> 5] = mn[c];
+            smax[c][threadIdx.x >> 5] = mx[c];
+        }
+    }
+    __syncthreads();
+    if(threadIdx.x < 3) {
+        int c = threadIdx.x;
+        double a = smin[c][0], b = smax[c][0];
+        for(int w = 1; w < kThreads / 32; ++w) {
+            a = fmin(a, smin[c][w]);
+            b = fmax(b, smax[c][w]);
+        }
+        out[blockIdx.x * 6 + c] = a;
+        out[blockIdx.x * 6 + 3 + c] = b;
+    }
+}
+
+__global__ void bin_count_kernel(const double* __restrict__ xyz, uint32_t n, GridDesc G,
+                                 uint32_t* __restrict__ cellid, uint32_t* __restrict__ rank,
+                                 uint32_t* __restrict__ counts) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) {
+        return;
+    }
+    double x = xyz[3 * size_t(i)], y = xyz[3 * size_t(i) + 1], z = xyz[3 * size_t(i) + 2];
+    int ix, iy, iz;
+    cell_coords(G, x, y, z, ix, iy, iz);
+    uint32_t c = uint32_t(ix) + uint32_t(G.g[0]) * (uint32_t(iy) + uint32_t(G.g[1]) * uint32_t(iz));
+    cellid[i] = c;
+    rank[i] = atomicAdd(&counts[c], 1u);
+}
+
+// ---- exclusive scan of uint32 (three phases, 4096 items per block) ----
+constexpr int kScanItems = 16;
+constexpr int kScanTile = kThreads * kScanItems;
+
+__device__ inline uint32_t block_exclusive_scan(uint32_t v, uint32_t* total) {
+    __shared__ uint32_t wsum[kThreads / 32];
+    uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t inc = v;
+    for(int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if(lane >= uint32_t(o)) {
+            inc += t;
+        }
+    }
+    if(lane == 31) {
+        wsum[wid] = inc;
+    }
+    __syncthreads();
+    if(wid == 0) {
+        uint32_t s = lane < kThreads / 32 ? wsum[lane] : 0;
+        for(int o = 1; o < kThreads / 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, s, o);
+            if(lane >= uint32_t(o)) {
+                s += t;
+            }
+        }
+        if(lane < kThreads / 32) {
+            wsum[lane] = s;
+        }
+    }
+    __syncthreads();
+    uint32_t base = wid ? wsum[wid - 1] : 0;
+    if(total) {
+        *total = wsum[kThreads / 32 - 1];
+    }
+    __syncthreads();
+    return base + inc - v;
+}
+
+__global__ void scan_tile_sums(const uint32_t* __restrict__ in, uint32_t n,
+                               uint32_t* __restrict__ tile_sums) {
+    size_t base = size_t(blockIdx.x) * kScanTile + size_t(threadIdx.x) * kScanItems;
+    uint32_t s = 0;
+    for(int k = 0; k < kScanItems; ++k) {
+        if(base + k < n) {
+            s += in[base + k];
+        }
+    }
+    uint32_t total;
+    block_exclusive_scan(s, &total);
+    if(threadIdx.x == 0) {
+        tile_sums[blockIdx.x] = total;
+    }
+}
+
+__global__ void scan_of_sums(uint32_t* tile_sums, uint32_t ntiles) {
+    // single block: in-place exclusive scan, chunk by chunk
+    __shared__ uint32_t carry;
+    if(threadIdx.x == 0) {
+        carry = 0;
+    }
+    __syncthreads();
+    for(uint32_t b = 0; b < ntiles; b += kThreads) {
+        uint32_t i = b + threadIdx.x;
+        uint32_t v = i < ntiles ? tile_sums[i] : 0;
+        uint32_t total;
+        uint32_t ex = block_exclusive_scan(v, &total);
+        uint32_t c = carry;
+        if(i < ntiles) {
+            tile_sums[i] = c + ex;
+        }
+        __syncthreads();
+        if(threadIdx.x == 0) {
+            carry = c + total;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void scan_apply(const uint32_t* __restrict__ in, uint32_t n,
+                           const uint32_t* __restrict__ tile_sums,
+                           uint32_t* __restrict__ out, uint32_t total_n) {
+    size_t base = size_t(blockIdx.x) * kScanTile + size_t(threadIdx.x) * kScanItems;
+    uint32_t v[kScanItems];
+    uint32_t s = 0;
+    for(int k = 0; k < kScanItems; ++k) {
+        v[k] = (base + k < n) ? in[base + k] : 0;
+        s += v[k];
+    }
+    uint32_t ex = block_exclusive_scan(s, nullptr) + tile_sums[blockIdx.x];
+    for(int k = 0; k < kScanItems; ++k) {
+        if(base + k < n) {
+            out[base + k] = ex;
+        }
+        ex += v[k];
+    }
+    if(blockIdx.x == 0 && threadIdx.x == 0) {
+        out[n] = total_n;
+    }
+}
+
+__global__ void bin_scatter_kernel(const double* __restrict__ xyz,
+                                   const double* __restrict__ w, uint32_t n,
+                                   const uint32_t* __restrict__ cellid,
+                                   const uint32_t* __restrict__ rank,
+                                   const uint32_t* __restrict__ cell_start,
+                                   Seed* __restrict__ sorted, uint32_t* __restrict__ perm) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) {
+        return;
+    }
+    uint32_t pos = cell_start[cellid[i]] + rank[i];
+    double x = xyz[3 * size_t(i)], y = xyz[3 * size_t(i) + 1], z = xyz[3 * size_t(i) + 2];
+    double ww = w ? w[i] : 0.0;
+    double2* dst = reinterpret_cast<double2*>(sorted + pos);
+    dst[0] = make_double2(x, y);
+    dst[1] = make_double2(z, ww);
+    perm[pos] = i;
+}
+
+}  // namespace
+
+int build_grid(Ctx* c) {
+    const uint32_t n = c->n;
+    cudaStream_t st = c->stream;
+    GridDesc& G = c->grid;
+    G.periodic = c->periodic;
+    G.period = c->period;
+    double lo[3], hi[3];
+    if(c->periodic) {
+        for(int a = 0; a < 3; ++a) {
+            lo[a] = 0.0;
+            hi[a] = c->period;
+        }
+    } else {
+        const int nb = 296;
+        if(int rc0 = c->scan_tmp.reserve(size_t(nb) * 6 * 2 + 64)) {
+            return rc0;
+        }
+        double* part = reinterpret_cast<double*>(c->scan_tmp.p);
+        bbox_kernel<<<nb, kThreads, 0, st>>>(c->xyz.p, n, part);
+        c->stats.gpu_launches++;
+        double host[nb * 6];
+        B200_CUDA_CHECK(cudaMemcpyAsync(host, part, sizeof(host), cudaMemcpyDeviceToHost, st));
+        B200_CUDA_CHECK(cudaStreamSynchronize(st));
+        for(int a = 0; a < 3; ++a) {
+            lo[a] = 1e300;
+            hi[a] = -1e300;
+        }
+        for(int b = 0; b < nb; ++b) {
+            for(int a = 0; a < 3; ++a) {
+                lo[a] = fmin(lo[a], host[b * 6 + a]);
+                hi[a] = fmax(hi[a], host[b * 6 + 3 + a]);
+            }
+        }
+    }
+    double ext[3], vol = 1.0;
+    double maxext = 0.0;
+    for(int a = 0; a < 3; ++a) {
+        ext[a] = hi[a] - lo[a];
+        maxext = fmax(maxext, ext[a]);
+    }
+    if(!(maxext > 0.0)) {
+        maxext = 1.0;
+    }
+    for(int a = 0; a < 3; ++a) {
+        if(!(ext[a] > 1e-9 * maxext)) {
+            ext[a] = 1e-9 * maxext;   // flat direction: one layer of cells
+        }
+        vol *= ext[a];
+    }
+    double target = fmax(1.0, double(n) / c->ppc);
+    double width = cbrt(vol / target);
+    uint64_t ncell = 1;
+    for(int a = 0; a < 3; ++a) {
+        int g = int(floor(ext[a] / width + 0.5));
+        if(g < 1) {
+            g = 1;
+        }
+        if(g > 2048) {
+            g = 2048;
+        }
+        G.g[a] = g;
+        G.lo[a] = lo[a];
+        G.w[a] = ext[a] / g;
+        G.inv_w[a] = g / ext[a];
+        ncell *= uint64_t(g);
+    }
+    G.ncell = uint32_t(ncell);
+    c->stats.grid_dim[0] = G.g[0];
+    c->stats.grid_dim[1] = G.g[1];
+    c->stats.grid_dim[2] = G.g[2];
+
+    int rc;
+    if((rc = c->cellid.reserve(n)) || (rc = c->rank.reserve(n)) ||
+       (rc = c->perm.reserve(n)) || (rc = c->sorted.reserve(n)) ||
+       (rc = c->cell_start.reserve(size_t(G.ncell) + 1))) {
+        return rc;
+    }
+    uint32_t ntiles = (G.ncell + kScanTile - 1) / kScanTile;
+    // counters live after the tile sums in scan_tmp
+    if((rc = c->scan_tmp.reserve(size_t(ntiles) + size_t(G.ncell) + 4096))) {
+        return rc;
+    }
+    uint32_t* tile_sums = c->scan_tmp.p;
+    uint32_t* counts = c->scan_tmp.p + ntiles + 1;
+    B200_CUDA_CHECK(cudaMemsetAsync(counts, 0, size_t(G.ncell) * sizeof(uint32_t), st));
+    uint32_t nblk = (n + kThreads - 1) / kThreads;
+    bin_count_kernel<<<nblk, kThreads, 0, st>>>(c->xyz.p, n, G, c->cellid.p, c->rank.p, counts);
+    scan_tile_sums<<<ntiles, kThreads, 0, st>>>(counts, G.ncell, tile_sums);
+    scan_of_sums<<<1, kThreads, 0, st>>>(tile_sums, ntiles);
+    scan_apply<<<ntiles, kThreads, 0, st>>>(counts, G.ncell, tile_sums, c->cell_start.p, n);
+    bin_scatter_kernel<<<nblk, kThreads, 0, st>>>(c->xyz.p, c->has_w ? c->wgt.p : nullptr, n,
+                                                  c->cellid.p, c->rank.p, c->cell_start.p,
+                                                  c->sorted.p, c->perm.p);
+    c->stats.gpu_launches += 5;
+    B200_CUDA_CHECK(cudaGetLastError());
+    return B200VOR_OK;
+}
+
+}  // namespace b200vor

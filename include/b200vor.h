@@ -1,0 +1,136 @@
+/*
+ * b200vor.h -- C ABI of the B200-native meshless Voronoi / Laguerre cell engine.
+ *
+ * This is the drop-in boundary: plain pointers and sizes,
+ * caller-owned buffers, int return codes (0 = success, else see
+ * b200vor_last_error()).  No C++ or torch type crosses it.  The C++ host classes in
+ * geogram_b200/host/ (mirrors of GEO::NearestNeighborSearch,
+ * GEO::Delaunay_NearestNeighbors, VBW::ConvexCell batch output and the Lloyd driver)
+ * and the reference-side plugin shown in INTEGRATION.md call only these entry points.
+ *
+ * Every buffer argument comes with `on_device`: 0 = host memory (the call copies
+ * across PCIe inside), 1 = device memory on the context's GPU (no copy).
+ *
+ * Reference interfaces replaced (paths relative to /root/reference/src/lib/geogram):
+ *   b200vor_set_points       NearestNeighborSearch::set_points      points/nn_search.h:98-123
+ *                            Delaunay::set_vertices                 delaunay/delaunay.h:259
+ *                            PeriodicDelaunay3d::set_weights        delaunay/periodic_delaunay_3d.h:151
+ *   b200vor_knn              NearestNeighborSearch::get_nearest_neighbors (by index)
+ *                                                                   points/nn_search.h:180-185
+ *                            Delaunay::update_neighbors             delaunay/delaunay.cpp:259-274
+ *   b200vor_knn_points       NearestNeighborSearch::get_nearest_neighbors (by point)
+ *                                                                   points/nn_search.h:129-134
+ *   b200vor_compute_cells    clip_by_cell_SR                        voronoi/generic_RVD.h:2278-2347
+ *                            ConvexCell::clip_by_plane / compute_mg voronoi/convex_cell.cpp:467, :1267
+ *                            PeriodicDelaunay3d::copy_Laguerre_cell_from_Delaunay
+ *                                                                   delaunay/periodic_delaunay_3d.cpp:3634
+ *   b200vor_get_cells        RestrictedVoronoiDiagram::compute_centroids (mg, m)
+ *                                                                   voronoi/RVD.h:284-290
+ *   b200vor_get_faces        ConvexCell::v_global_index / facet_area voronoi/convex_cell.h:463, convex_cell.cpp:1160
+ *   b200vor_lloyd            CentroidalVoronoiTesselation::Lloyd_iterations
+ *                                                                   voronoi/CVT.cpp:133-169
+ */
+#ifndef B200VOR_H
+#define B200VOR_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200VOR_VERSION 1
+
+typedef struct b200vor_ctx b200vor_ctx;
+
+/* ---- return codes ---- */
+#define B200VOR_OK            0
+#define B200VOR_ERR_CUDA      1   /* a CUDA call failed (no GPU, OOM, launch error) */
+#define B200VOR_ERR_ARG       2   /* invalid argument / call order                  */
+#define B200VOR_ERR_CAPACITY  3   /* a fixed capacity was exceeded                  */
+
+/* ---- per-cell status bits (b200vor_get_cells status[]) ---- */
+#define B200VOR_CELL_OK          0u
+#define B200VOR_CELL_UNCERTIFIED 1u   /* security radius not reached within kmax / ring limit */
+#define B200VOR_CELL_UNCERTAIN   2u   /* a sign test fell inside the fp64 error bound          */
+#define B200VOR_CELL_EMPTY       4u   /* (Laguerre) cell clipped away entirely                 */
+#define B200VOR_CELL_BOXFACE     8u   /* periodic: a helper-box plane still contributes        */
+#define B200VOR_CELL_OVERFLOW    16u  /* more than the kernel's triangle / plane capacity      */
+#define B200VOR_CELL_DUPLICATE   32u  /* exact duplicate of a lower-index seed: no cell
+                                         (delaunay/delaunay_nn.cpp:122-135)                    */
+
+/* ids of the six planes of the clipping box in face lists: B200VOR_BOX_ID + {x-,x+,y-,y+,z-,z+} */
+#define B200VOR_BOX_ID 0xFFFFFFF0u
+
+typedef struct b200vor_cell_params {
+    uint32_t k0;          /* neighbours fetched in the first pass (0 = default 48)            */
+    uint32_t kmax;        /* cap on k for the re-launches of uncertified cells (0 = 384)      */
+    uint32_t want_faces;  /* 1: keep per-cell face lists (+ areas) for b200vor_get_faces      */
+    uint32_t mode;        /* 0 = kNN table -> clipper (re-launch failing cells with larger k)
+                             1 = fused grid walk (no kNN table)                               */
+} b200vor_cell_params;
+
+typedef struct b200vor_stats {
+    /* device milliseconds of the last b200vor_set_points / b200vor_compute_cells */
+    float ms_grid, ms_knn, ms_clip, ms_total;
+    uint32_t passes;                 /* kNN+clip passes (1 + re-launches)            */
+    uint32_t n_pass[8];              /* cells processed in each pass                 */
+    uint32_t k_pass[8];              /* k of each pass                               */
+    uint32_t n_uncertified, n_uncertain, n_empty, n_boxface, n_overflow, n_duplicate;
+    /* event counts of the SURVEY 8(d) flop model, summed over cells (last pass of each cell) */
+    uint64_t sum_planes;             /* P: planes offered before the security-radius stop */
+    uint64_t sum_tests;              /* C: triangle sign tests                            */
+    uint64_t sum_created;            /* V: triangles created                              */
+    uint64_t sum_tets;               /* I: integration terms                              */
+    uint64_t gpu_launches;           /* kernels launched by this context so far           */
+    uint32_t grid_dim[3];
+    uint32_t reserved;
+} b200vor_stats;
+
+/* ---- life cycle ---- */
+int  b200vor_create(b200vor_ctx** ctx, int device);
+void b200vor_destroy(b200vor_ctx* ctx);
+const char* b200vor_last_error(void);
+int  b200vor_version(void);
+
+/* ---- domain ---- */
+/* cells are clipped by box = {xmin,ymin,zmin,xmax,ymax,zmax} (default: unit cube) */
+int b200vor_set_domain_box(b200vor_ctx* ctx, const double* box);
+/* periodic cube [0,period)^3; neighbour ids become real + n*instance (periodic.h:95-99) */
+int b200vor_set_domain_periodic(b200vor_ctx* ctx, double period);
+
+/* ---- points (copied; builds the uniform grid) ---- */
+/* xyz: n points, `stride` doubles apart (>= 3).  w: NULL or n weights (Laguerre). */
+int b200vor_set_points(b200vor_ctx* ctx, uint32_t n, const double* xyz, uint32_t stride,
+                       const double* w, int on_device);
+
+/* ---- kNN ---- */
+/* rows of k for every point (query by index), ascending squared distance, the point
+ * itself at rank 0, ties by ascending index.  d2 may be NULL. */
+int b200vor_knn(b200vor_ctx* ctx, uint32_t k, uint32_t* nbr, double* d2, int on_device);
+/* same for nq arbitrary query points (3 doubles each, contiguous) */
+int b200vor_knn_points(b200vor_ctx* ctx, uint32_t nq, const double* q, uint32_t k,
+                       uint32_t* nbr, double* d2, int on_device);
+
+/* ---- cells ---- */
+int b200vor_compute_cells(b200vor_ctx* ctx, const b200vor_cell_params* params);
+/* m[n], mg[3n] (mass and mass*centroid, as ConvexCell::compute_mg), status[n]; any may be NULL */
+int b200vor_get_cells(b200vor_ctx* ctx, double* m, double* mg, uint8_t* status, int on_device);
+/* nfaces[n], face_nbr[n*fcap] (ascending ids), face_area[n*fcap] (may be NULL) */
+int b200vor_get_faces(b200vor_ctx* ctx, uint32_t* nfaces, uint32_t* face_nbr,
+                      double* face_area, uint32_t fcap, int on_device);
+
+/* ---- Lloyd relaxation: iters x (grid, cells, p <- mg/m, periodic wrap) ---- */
+/* xyz_out (n x 3, may be NULL) receives the relaxed points */
+int b200vor_lloyd(b200vor_ctx* ctx, uint32_t iters, const b200vor_cell_params* params,
+                  double* xyz_out, int on_device);
+
+/* ---- introspection ---- */
+int b200vor_get_stats(b200vor_ctx* ctx, b200vor_stats* stats);
+/* tuning knob: target points per grid cell (default 4.0); takes effect at the next set_points */
+int b200vor_set_points_per_cell(b200vor_ctx* ctx, double ppc);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
