@@ -19,6 +19,7 @@ CELL_EMPTY = 4
 CELL_BOXFACE = 8
 CELL_OVERFLOW = 16
 CELL_DUPLICATE = 32
+CELL_DEGENERATE = 64
 FCAP = 64
 
 # every symbol include/b200vor.h declares
@@ -45,10 +46,11 @@ class Stats(ctypes.Structure):
         ("n_uncertified", ctypes.c_uint32), ("n_uncertain", ctypes.c_uint32),
         ("n_empty", ctypes.c_uint32), ("n_boxface", ctypes.c_uint32),
         ("n_overflow", ctypes.c_uint32), ("n_duplicate", ctypes.c_uint32),
+        ("n_degenerate", ctypes.c_uint32),
         ("sum_planes", ctypes.c_uint64), ("sum_tests", ctypes.c_uint64),
         ("sum_created", ctypes.c_uint64), ("sum_tets", ctypes.c_uint64),
         ("gpu_launches", ctypes.c_uint64),
-        ("grid_dim", ctypes.c_uint32 * 3), ("reserved", ctypes.c_uint32),
+        ("grid_dim", ctypes.c_uint32 * 3),
     ]
 
     def as_dict(self):

@@ -151,10 +151,31 @@ int cells_pipeline(Ctx* c, const b200vor_cell_params* params, bool collect_event
             return rc;
         }
         T.mark(2);
-        CellJob cj = {nq, qlist, rl, c->knn.p, c->knn_flag.p, int(p.want_faces),
+        CellJob cj = {nq, qlist, nullptr, 2, rl, c->knn.p, c->knn_flag.p, int(p.want_faces),
                       collect_events ? 1 : 0, int(p.mode)};
         if((rc = run_cells(c, cj))) {
             return rc;
+        }
+        // cells that outgrew the 64-triangle register table: same rows, 128-triangle kernel
+        {
+            if((rc = c->qlist3.reserve(nq)) || (rc = c->qrows.reserve(nq))) {
+                return rc;
+            }
+            uint32_t novf = 0;
+            if((rc = compact_failed(c, qlist, nq, c->qlist3.p, c->qrows.p, &novf,
+                                    B200VOR_CELL_OVERFLOW))) {
+                return rc;
+            }
+            if(novf) {
+                CellJob big = cj;
+                big.nq = novf;
+                big.qlist = c->qlist3.p;
+                big.rowmap = c->qrows.p;
+                big.slots = 4;
+                if((rc = run_cells(c, big))) {
+                    return rc;
+                }
+            }
         }
         T.mark(0);
         c->stats.n_pass[pass] = nq;
@@ -169,7 +190,7 @@ int cells_pipeline(Ctx* c, const b200vor_cell_params* params, bool collect_event
         }
         uint32_t* out = (qlist == c->qlist.p) ? c->qlist2.p : c->qlist.p;
         uint32_t nfail = 0;
-        if((rc = compact_failed(c, qlist, nq, out, &nfail, B200VOR_CELL_UNCERTIFIED))) {
+        if((rc = compact_failed(c, qlist, nq, out, nullptr, &nfail, B200VOR_CELL_UNCERTIFIED))) {
             return rc;
         }
         qlist = out;
@@ -247,7 +268,7 @@ void b200vor_destroy(b200vor_ctx* h) {
     cudaStreamSynchronize(c.stream);
     c.xyz.release(); c.wgt.release(); c.cellid.release(); c.rank.release();
     c.cell_start.release(); c.perm.release(); c.scan_tmp.release(); c.sorted.release();
-    c.knn.release(); c.knn_flag.release(); c.qlist.release(); c.qlist2.release();
+    c.knn.release(); c.knn_flag.release(); c.qlist.release(); c.qlist2.release(); c.qlist3.release(); c.qrows.release();
     c.counter.release(); c.m.release(); c.mg.release(); c.status.release();
     c.nfaces.release(); c.face_nbr.release(); c.face_area.release(); c.evcount.release();
     c.sums.release(); c.out_nbr.release(); c.out_d2.release(); c.qpts.release();

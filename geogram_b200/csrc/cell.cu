@@ -280,7 +280,7 @@ template <int S> struct WarpCell {
             if(valid && !cf[s]) {
 #pragma unroll
                 for(int e = 0; e < 3; ++e) {
-                    uint32_t o = (adj[s] >> (8 * e)) & 0xffu;
+                    uint32_t o = (adj[s] >> (8 * e)) & uint32_t(NT - 1);
                     if(conflict_bit(cm, o)) {
                         bits |= 1u << (3 * s + e);
                     }
@@ -421,7 +421,7 @@ __device__ inline void integrate(WarpCell<S>& C, const CellParams& P, const Seed
 #pragma unroll
             for(int l = 0; l < 3; ++l) {
                 uint32_t f = (C.tri[s] >> (8 * l)) & 0xffu;
-                uint32_t nb = (C.adj[s] >> (8 * ((l + 1) % 3))) & 0xffu;
+                uint32_t nb = (C.adj[s] >> (8 * ((l + 1) % 3))) & uint32_t(32 * S - 1);
                 const double* v = sh->vtx + 3 * nb;
                 double vx = v[0], vy = v[1], vz = v[2];
                 const double* pf = sh->pl + 4 * f;
@@ -521,12 +521,47 @@ __device__ inline bool any_box_face(WarpCell<S>& C) {
     return __any_sync(kFull, mine);
 }
 
+// Integrity of the dual triangulation: Euler's relation T = 2F - 4 and symmetric
+// adjacency.  Fails only when uncertain sign tests produced a conflict zone that is
+// not a disk (degenerate input).
+template <int S>
+__device__ inline bool consistent(WarpCell<S>& C) {
+    constexpr uint32_t NT = 32 * S;
+    uint32_t T = 0;
+#pragma unroll
+    for(int s = 0; s < S; ++s) {
+        T += __popc(C.vmask[s]);
+        C.sh->rec[C.lane + 32 * s] = ((C.vmask[s] >> C.lane) & 1u) ? C.adj[s] : 0xffffffffu;
+    }
+    __syncwarp();
+    uint32_t F = __popcll(C.used_planes());
+    bool ok = true;
+#pragma unroll
+    for(int s = 0; s < S; ++s) {
+        if((C.vmask[s] >> C.lane) & 1u) {
+            uint32_t me = C.lane + 32 * s;
+#pragma unroll
+            for(int e = 0; e < 3; ++e) {
+                uint32_t nb = (C.adj[s] >> (8 * e)) & 0xffu;
+                uint32_t back = nb < NT ? C.sh->rec[nb] : 0xffffffffu;
+                bool sym = back != 0xffffffffu &&
+                           ((back & 0xffu) == me || ((back >> 8) & 0xffu) == me ||
+                            ((back >> 16) & 0xffu) == me);
+                ok = ok && sym;
+            }
+        }
+    }
+    ok = __all_sync(kFull, ok);
+    __syncwarp();
+    return ok && (T + 4 == 2 * F);
+}
+
 // ---- mode 0: candidates come from the kNN table, ascending distance ----
-template <int S, bool FACES>
-__global__ void __launch_bounds__(32 * kWarpsPerBlock) cells_knn_kernel(CellParams P) {
-    __shared__ SharedLayout<S> shared[kWarpsPerBlock];
+template <int S, bool FACES, int WPB>
+__global__ void __launch_bounds__(32 * WPB) cells_knn_kernel(CellParams P) {
+    __shared__ SharedLayout<S> shared[WPB];
     const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
-    const uint32_t c = blockIdx.x * kWarpsPerBlock + wid;
+    const uint32_t c = blockIdx.x * WPB + wid;
     if(c >= P.job.nq) {
         return;
     }
@@ -550,7 +585,8 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) cells_knn_kernel(CellPara
     C.init_box(bx);
 
     const uint32_t k = P.job.k;
-    const uint32_t* nrow = P.job.knn + size_t(c) * k;
+    const uint32_t trow = P.job.rowmap ? P.job.rowmap[c] : c;
+    const uint32_t* nrow = P.job.knn + size_t(trow) * k;
     const double dw = P.has_w ? (P.wmax - si.w) : 0.0;
     bool certified = false, done = false;
     uint32_t extra = 0;
@@ -621,7 +657,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) cells_knn_kernel(CellPara
         }
     }
     C.status |= extra;
-    if(P.job.knn_flag && P.job.knn_flag[c]) {
+    if(P.job.knn_flag && P.job.knn_flag[trow]) {
         certified = false;
     }
     if(!certified) {
@@ -629,6 +665,9 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) cells_knn_kernel(CellPara
     }
     if(P.periodic && !(C.status & B200VOR_CELL_EMPTY) && any_box_face(C)) {
         C.status |= B200VOR_CELL_BOXFACE;
+    }
+    if(!(C.status & B200VOR_CELL_EMPTY) && !consistent(C)) {
+        C.status |= B200VOR_CELL_DEGENERATE;
     }
     uint32_t ntri;
     integrate<S, FACES>(C, P, si, row, ntri);
@@ -645,7 +684,9 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) cells_knn_kernel(CellPara
 __global__ void compact_kernel(const uint32_t* __restrict__ qin, uint32_t nq,
                                const uint32_t* __restrict__ perm,
                                const uint8_t* __restrict__ status, uint8_t mask,
-                               uint32_t* __restrict__ qout, uint32_t* __restrict__ counter) {
+                               uint32_t* __restrict__ qout, uint32_t* __restrict__ rows_out,
+                               const uint32_t* __restrict__ rows_in,
+                               uint32_t* __restrict__ counter) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     bool fail = false;
     uint32_t i = 0;
@@ -662,7 +703,11 @@ __global__ void compact_kernel(const uint32_t* __restrict__ qin, uint32_t nq,
     }
     base = __shfl_sync(kFull, base, 0);
     if(fail) {
-        qout[base + __popc(bal & ((1u << lane) - 1u))] = i;
+        uint32_t pos = base + __popc(bal & ((1u << lane) - 1u));
+        qout[pos] = i;
+        if(rows_out) {
+            rows_out[pos] = rows_in ? rows_in[t] : t;
+        }
     }
 }
 
@@ -695,7 +740,7 @@ __global__ void reduce_events_kernel(uint32_t n, const uint32_t* __restrict__ ev
                                      const uint8_t* __restrict__ status,
                                      unsigned long long* __restrict__ sums) {
     // sums: 0..3 = P, C, V, I ; 4.. = status bit counts (6 bits)
-    unsigned long long acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned long long acc[11] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         if(ev) {
             uint32_t a = ev[2 * size_t(i)], b = ev[2 * size_t(i) + 1];
@@ -705,11 +750,11 @@ __global__ void reduce_events_kernel(uint32_t n, const uint32_t* __restrict__ ev
             acc[3] += 3ull * (b >> 20);
         }
         uint8_t s = status[i];
-        for(int k = 0; k < 6; ++k) {
+        for(int k = 0; k < 7; ++k) {
             acc[4 + k] += (s >> k) & 1u;
         }
     }
-    for(int k = 0; k < 10; ++k) {
+    for(int k = 0; k < 11; ++k) {
         unsigned long long v = acc[k];
         for(int o = 16; o > 0; o >>= 1) {
             v += __shfl_xor_sync(kFull, v, o);
@@ -748,11 +793,21 @@ int run_cells(Ctx* c, const CellJob& job) {
     P.face_area = c->face_area.p;
     P.fcap = c->fcap;
     P.evcount = job.collect_events ? c->evcount.p : nullptr;
-    uint32_t nblk = (job.nq + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    if(job.want_faces) {
-        cells_knn_kernel<2, true><<<nblk, 32 * kWarpsPerBlock, 0, c->stream>>>(P);
+    if(job.slots == 4) {
+        constexpr int W4 = 4;
+        uint32_t nblk = (job.nq + W4 - 1) / W4;
+        if(job.want_faces) {
+            cells_knn_kernel<4, true, W4><<<nblk, 32 * W4, 0, c->stream>>>(P);
+        } else {
+            cells_knn_kernel<4, false, W4><<<nblk, 32 * W4, 0, c->stream>>>(P);
+        }
     } else {
-        cells_knn_kernel<2, false><<<nblk, 32 * kWarpsPerBlock, 0, c->stream>>>(P);
+        uint32_t nblk = (job.nq + kWarpsPerBlock - 1) / kWarpsPerBlock;
+        if(job.want_faces) {
+            cells_knn_kernel<2, true, kWarpsPerBlock><<<nblk, 32 * kWarpsPerBlock, 0, c->stream>>>(P);
+        } else {
+            cells_knn_kernel<2, false, kWarpsPerBlock><<<nblk, 32 * kWarpsPerBlock, 0, c->stream>>>(P);
+        }
     }
     c->stats.gpu_launches++;
     B200_CUDA_CHECK(cudaGetLastError());
@@ -760,7 +815,7 @@ int run_cells(Ctx* c, const CellJob& job) {
 }
 
 int compact_failed(Ctx* c, const uint32_t* qlist_in, uint32_t nq_in, uint32_t* qlist_out,
-                   uint32_t* count_out_host, uint8_t mask) {
+                   uint32_t* rows_out, uint32_t* count_out_host, uint8_t mask) {
     int rc = c->counter.reserve(4);
     if(rc) {
         return rc;
@@ -768,7 +823,7 @@ int compact_failed(Ctx* c, const uint32_t* qlist_in, uint32_t nq_in, uint32_t* q
     B200_CUDA_CHECK(cudaMemsetAsync(c->counter.p, 0, sizeof(uint32_t), c->stream));
     uint32_t nblk = (nq_in + 255) / 256;
     compact_kernel<<<nblk, 256, 0, c->stream>>>(qlist_in, nq_in, c->perm.p, c->status.p, mask,
-                                                qlist_out, c->counter.p);
+                                                qlist_out, rows_out, nullptr, c->counter.p);
     c->stats.gpu_launches++;
     B200_CUDA_CHECK(cudaMemcpyAsync(count_out_host, c->counter.p, sizeof(uint32_t),
                                     cudaMemcpyDeviceToHost, c->stream));
@@ -807,6 +862,7 @@ int reduce_events(Ctx* c) {
     c->stats.n_boxface = uint32_t(h[7]);
     c->stats.n_overflow = uint32_t(h[8]);
     c->stats.n_duplicate = uint32_t(h[9]);
+    c->stats.n_degenerate = uint32_t(h[10]);
     return B200VOR_OK;
 }
 

@@ -116,7 +116,7 @@ struct Ctx {
     // kNN table of the cell pipeline (rows in pass order, ids in grid order + n*instance)
     DevBuf<uint32_t> knn;
     DevBuf<uint8_t> knn_flag;
-    DevBuf<uint32_t> qlist, qlist2, counter;
+    DevBuf<uint32_t> qlist, qlist2, qlist3, qrows, counter;
 
     // cell outputs, user order
     DevBuf<double> m, mg;
@@ -154,6 +154,8 @@ int run_knn(Ctx* c, const KnnJob& job);
 struct CellJob {
     uint32_t nq;
     const uint32_t* qlist;   // grid-order indices, or NULL
+    const uint32_t* rowmap;  // row of entry t in the kNN table, or NULL (= t)
+    int slots;               // triangle slots per lane: 2 (64 triangles) or 4 (128)
     uint32_t k;              // row length of the kNN table
     const uint32_t* knn;
     const uint8_t* knn_flag;
@@ -163,7 +165,7 @@ struct CellJob {
 };
 int run_cells(Ctx* c, const CellJob& job);
 int compact_failed(Ctx* c, const uint32_t* qlist_in, uint32_t nq_in, uint32_t* qlist_out,
-                   uint32_t* count_out_host, uint8_t mask);
+                   uint32_t* rows_out, uint32_t* count_out_host, uint8_t mask);
 int lloyd_update(Ctx* c);
 int reduce_events(Ctx* c);
 

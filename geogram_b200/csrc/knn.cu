@@ -132,15 +132,18 @@ __device__ inline void scan_row(const KnnParams& P, Heap<kStride>& H, int xa, in
     }
     if(G.periodic) {
         if(xa < 0) {
+            // cells [xa, min(xb,-1)] seen through the -x image
+            int hi = (xb < 0 ? xb : -1) + gx;
             uint32_t off = P.n * translation_to_instance(-1, sy, sz);
-            scan_span(P, H, __ldg(P.cell_start + row_base + xa + gx),
-                      __ldg(P.cell_start + row_base + gx), qx, qy, qz, -G.period, oy, oz,
+            scan_span(P, H, __ldg(P.cell_start + row_base + (xa + gx)),
+                      __ldg(P.cell_start + row_base + hi + 1), qx, qy, qz, -G.period, oy, oz,
                       off);
         }
         if(xb >= gx) {
+            int lo = (xa >= gx ? xa : gx) - gx;
             uint32_t off = P.n * translation_to_instance(1, sy, sz);
-            scan_span(P, H, __ldg(P.cell_start + row_base),
-                      __ldg(P.cell_start + row_base + xb - gx + 1), qx, qy, qz, G.period,
+            scan_span(P, H, __ldg(P.cell_start + row_base + lo),
+                      __ldg(P.cell_start + row_base + (xb - gx) + 1), qx, qy, qz, G.period,
                       oy, oz, off);
         }
     }

@@ -58,6 +58,8 @@ typedef struct b200vor_ctx b200vor_ctx;
 #define B200VOR_CELL_OVERFLOW    16u  /* more than the kernel's triangle / plane capacity      */
 #define B200VOR_CELL_DUPLICATE   32u  /* exact duplicate of a lower-index seed: no cell
                                          (delaunay/delaunay_nn.cpp:122-135)                    */
+#define B200VOR_CELL_DEGENERATE  64u  /* inconsistent combinatorics after uncertain sign tests
+                                         (degenerate input); m, mg are best-effort             */
 
 /* ids of the six planes of the clipping box in face lists: B200VOR_BOX_ID + {x-,x+,y-,y+,z-,z+} */
 #define B200VOR_BOX_ID 0xFFFFFFF0u
@@ -76,7 +78,8 @@ typedef struct b200vor_stats {
     uint32_t passes;                 /* kNN+clip passes (1 + re-launches)            */
     uint32_t n_pass[8];              /* cells processed in each pass                 */
     uint32_t k_pass[8];              /* k of each pass                               */
-    uint32_t n_uncertified, n_uncertain, n_empty, n_boxface, n_overflow, n_duplicate;
+    uint32_t n_uncertified, n_uncertain, n_empty, n_boxface, n_overflow, n_duplicate,
+             n_degenerate;
     /* event counts of the SURVEY 8(d) flop model, summed over cells (last pass of each cell) */
     uint64_t sum_planes;             /* P: planes offered before the security-radius stop */
     uint64_t sum_tests;              /* C: triangle sign tests                            */
@@ -84,7 +87,6 @@ typedef struct b200vor_stats {
     uint64_t sum_tets;               /* I: integration terms                              */
     uint64_t gpu_launches;           /* kernels launched by this context so far           */
     uint32_t grid_dim[3];
-    uint32_t reserved;
 } b200vor_stats;
 
 /* ---- life cycle ---- */

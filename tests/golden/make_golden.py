@@ -1,0 +1,88 @@
+"""Generates tests/golden/*.npz from the UNMODIFIED reference (oracle/_ref/libgeoref.so,
+built from /root/reference by oracle/Makefile).  Run in the build container:
+
+    python tests/golden/make_golden.py
+
+The fixtures pin (a) the CPU restatement oracle/voro_oracle.cpp (tests/test_oracle.py)
+and (b) the CUDA path (tests/test_gpu_parity.py) to outputs of the reference itself,
+because the reference ships no known-answer vectors for this path.
+Face lists are stored as CSR (ptr, ids) to keep the files small.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+import oracles  # noqa: E402
+
+
+def csr(R):
+    ptr = np.zeros(R.n + 1, np.int64)
+    ptr[1:] = np.cumsum(R.nfaces)
+    ids = np.concatenate([R.faces(i) for i in range(R.n)]).astype(np.uint32)
+    return ptr, ids
+
+
+def save_cells(name, xyz, R, w=None, **meta):
+    ptr, ids = csr(R)
+    d = dict(xyz=xyz, m=R.m, mg=R.mg, face_ptr=ptr, face_ids=ids)
+    if R.face_area is not None:
+        d["face_area"] = np.concatenate([R.face_area[i, : R.nfaces[i]] for i in range(R.n)])
+    if w is not None:
+        d["w"] = w
+    for k, v in meta.items():
+        d[k] = np.asarray(v)
+    np.savez_compressed(os.path.join(HERE, name), **d)
+    print(name, "n=%d sum(m)=%.15f mean faces=%.3f" % (R.n, R.m.sum(), R.nfaces.mean()))
+
+
+def main():
+    oracles.build_reference()
+    R = oracles.Reference()
+    # kNN: BalancedKdTree, by index (k=21 = reference default 20 + self) and by point
+    xyz = oracles.uniform_seeds(3000, 12345)
+    nbr, d2 = R.knn(xyz, 21)
+    q = np.random.default_rng(7).random((500, 3)) * 1.2 - 0.1
+    nbq, d2q = R.knn(xyz, 9, queries=q)
+    np.savez_compressed(os.path.join(HERE, "knn_uniform_3000.npz"), xyz=xyz, nbr=nbr, d2=d2,
+                        q=q, nbr_q=nbq, d2_q=d2q)
+    print("knn_uniform_3000.npz")
+    # config 1 shape: uniform seeds, unit box.  Oracle A (exact Delaunay) and oracle B
+    # (kNN + VBW::ConvexCell + security radius, k0=20) must agree; store A + B's stats.
+    A = R.cells_delaunay(xyz, areas=True)
+    B = R.cells_knn(xyz, k0=20)
+    assert oracles.face_mismatches(A, B) == 0
+    save_cells("cells_box_uniform_3000.npz", xyz, A, kstop_B=B.kstop, stats_B=B.stats)
+    # config 2 shape: periodic unit cube (ids = real + n*instance)
+    A = R.cells_delaunay(xyz, periodic=True, areas=True)
+    save_cells("cells_periodic_uniform_3000.npz", xyz, A)
+    # config 3 shape: Laguerre cells, periodic, w = a h^2 U(0,1), a = 0.02 (non-emptying)
+    n = xyz.shape[0]
+    h = n ** (-1.0 / 3.0)
+    w = 0.02 * h * h * np.random.default_rng(5).random(n)
+    A = R.cells_delaunay(xyz, w=w, periodic=True, areas=True)
+    assert A is not None
+    save_cells("cells_periodic_laguerre_3000.npz", xyz, A, w=w)
+    # Laguerre in a box, larger weights on Lloyd-relaxed seeds is covered on the GPU side;
+    # here: box + weights
+    A = R.cells_delaunay(xyz, w=w, areas=True)
+    assert A is not None
+    save_cells("cells_box_laguerre_3000.npz", xyz, A, w=w)
+    # config 4 shape: clustered seeds in a box (kNN + SR alone cannot certify the fringe)
+    xc = oracles.clustered_seeds(4000, 12345)
+    A = R.cells_delaunay(xc, areas=False)
+    save_cells("cells_box_clustered_4000.npz", xc, A)
+    # two Lloyd iterations, periodic (demo_Delaunay3d/main.cpp:432-456 update rule)
+    x = xyz.copy()
+    P = oracles.Port()
+    for _ in range(2):
+        A = R.cells_delaunay(x, periodic=True)
+        x = P.lloyd_update(x, A.m, A.mg, True, 1.0)
+    np.savez_compressed(os.path.join(HERE, "lloyd2_periodic_3000.npz"), xyz0=xyz, xyz2=x)
+    print("lloyd2_periodic_3000.npz")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,289 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (include/b200vor.h), against
+(1) golden vectors generated from the unmodified reference, (2) the CPU oracles on fresh
+seeded inputs, (3) size-independent properties at BASELINE sizes.
+
+Tolerances (BASELINE.json north_star): face connectivity bit-exact; per-cell volume and
+centroid relative 1e-6 (the tests use 1e-9: both sides are fp64); total volume 1e-9.
+"""
+import numpy as np
+import pytest
+
+import oracles
+from conftest import Golden
+
+pytestmark = pytest.mark.gpu
+
+VOL_RTOL = 1e-9
+SUM_TOL = 1e-9
+
+
+class GpuCells(object):
+    def __init__(self, ctx):
+        self.m, self.mg, self.status = ctx.get_cells()
+        self.nfaces, self.face_nbr, self.face_area = ctx.get_faces()
+        self.fcap = 64
+        self.n = self.m.shape[0]
+
+
+@pytest.fixture(scope="module")
+def Context():
+    from geogram_b200 import Context as C
+    return C
+
+
+def run_cells(Context, xyz, w=None, periodic=False, **kw):
+    ctx = Context(0)
+    if periodic:
+        ctx.set_domain_periodic(1.0)
+    ctx.set_points(xyz, w)
+    ctx.compute_cells(want_faces=True, **kw)
+    return GpuCells(ctx), ctx
+
+
+def check(R, G, ok=None):
+    if ok is None:
+        ok = np.ones(G.n, bool)
+    col = np.arange(64)[None, :]
+    bad = (R.nfaces != G.nfaces) | (
+        (R.face_nbr != G.face_nbr[:, :64]) & (col < R.nfaces[:, None])).any(axis=1)
+    assert int((bad & ok).sum()) == 0, "face lists differ for %d cells" % (bad & ok).sum()
+    assert np.all(np.abs(R.m[ok] - G.m[ok]) <= VOL_RTOL * G.m[ok])
+    size = np.cbrt(G.m[ok])[:, None]
+    assert np.all(np.abs(R.mg[ok] - G.mg[ok]) <= 1e-9 * size * G.m[ok][:, None] + 1e-18)
+    if G.face_area is not None:
+        mask = (col < G.nfaces[:, None]) & ok[:, None]
+        assert np.allclose(R.face_area[mask], G.face_area[mask], rtol=1e-7, atol=1e-13)
+
+
+# ---------------------------------------------------------------- kNN
+def test_knn_golden(Context):
+    d = np.load(oracles.ROOT + "/tests/golden/knn_uniform_3000.npz")
+    ctx = Context(0)
+    ctx.set_points(d["xyz"])
+    nbr, d2 = ctx.knn(21)
+    assert (d2 == d["d2"]).all()      # bit-exact, as test_nn_search/main.cpp:169-181 demands
+    assert (nbr == d["nbr"]).all()
+    nbq, d2q = ctx.knn_points(d["q"], 9)
+    assert (d2q == d["d2_q"]).all()
+    assert (nbq == d["nbr_q"]).all()
+
+
+@pytest.mark.parametrize("n,k", [(100000, 21), (50000, 101), (20000, 200), (3000, 400)])
+def test_knn_vs_oracle(Context, port, n, k):
+    xyz = oracles.uniform_seeds(n, 1000 + k)
+    ctx = Context(0)
+    ctx.set_points(xyz)
+    nbr, d2 = ctx.knn(k)
+    nbr_o, d2_o = port.knn(xyz, k)
+    assert (d2 == d2_o).all()
+    assert (nbr == nbr_o).all()
+    assert (nbr[:, 0] == np.arange(n)).all()           # self at rank 0
+    assert (np.diff(d2, axis=1) >= 0).all()            # ascending
+
+
+def test_knn_clustered_and_flat(Context, port):
+    xyz = oracles.clustered_seeds(30000, 5)
+    ctx = Context(0)
+    ctx.set_points(xyz)
+    nbr, d2 = ctx.knn(21)
+    nbr_o, d2_o = port.knn(xyz, 21)
+    assert (d2 == d2_o).all() and (nbr == nbr_o).all()
+    flat = oracles.uniform_seeds(5000, 8)
+    flat[:, 2] = 0.25                                   # coplanar input
+    ctx.set_points(flat)
+    nbr, d2 = ctx.knn(16)
+    nbr_o, d2_o = port.knn(flat, 16)
+    assert (d2 == d2_o).all() and (nbr == nbr_o).all()
+
+
+def test_knn_ties_and_small(Context, port):
+    # lattice: massive exact ties; indices may differ (reference: traversal order), d2 must not
+    g = 9
+    ax = (np.arange(g) + 0.5) / g
+    xyz = np.stack(np.meshgrid(ax, ax, ax, indexing="ij"), -1).reshape(-1, 3).copy()
+    ctx = Context(0)
+    ctx.set_points(xyz)
+    nbr, d2 = ctx.knn(27)
+    nbr_o, d2_o = port.knn(xyz, 27)
+    assert (d2 == d2_o).all()
+    # tie order of this implementation: ascending index
+    same = d2[:, 1:] == d2[:, :-1]
+    assert (nbr[:, 1:][same] > nbr[:, :-1][same]).all()
+    # k == n
+    xyz = oracles.uniform_seeds(7, 3)
+    ctx.set_points(xyz)
+    nbr, d2 = ctx.knn(7)
+    nbr_o, d2_o = port.knn(xyz, 7)
+    assert (d2 == d2_o).all() and (nbr == nbr_o).all()
+    from geogram_b200 import B200VorError
+    with pytest.raises(B200VorError):
+        ctx.knn(8)                                       # k > n: geo_debug_assert in the reference
+
+
+# ---------------------------------------------------------------- cells, golden
+@pytest.mark.parametrize("name,periodic", [
+    ("cells_box_uniform_3000.npz", False),
+    ("cells_periodic_uniform_3000.npz", True),
+    ("cells_periodic_laguerre_3000.npz", True),
+    ("cells_box_laguerre_3000.npz", False),
+])
+def test_cells_golden(Context, name, periodic):
+    G = Golden(name)
+    R, ctx = run_cells(Context, G.xyz, G.w, periodic)
+    assert (R.status == 0).all(), np.bincount(R.status)
+    check(R, G)
+    assert abs(R.m.sum() - 1.0) < SUM_TOL
+
+
+def test_cells_clustered_golden(Context):
+    """Fringe cells of clustered seeds: certified cells must be exact, the others flagged."""
+    G = Golden("cells_box_clustered_4000.npz")
+    R, ctx = run_cells(Context, G.xyz)
+    ok = R.status == 0
+    assert ok.sum() > 0.8 * G.n
+    assert ((R.status & ~np.uint8(1)) == 0).all()        # only UNCERTIFIED may be set
+    check(R, G, ok)
+    R, ctx = run_cells(Context, G.xyz, kmax=570)
+    ok = R.status == 0
+    check(R, G, ok)
+
+
+def test_lloyd_golden(Context):
+    d = np.load(oracles.ROOT + "/tests/golden/lloyd2_periodic_3000.npz")
+    ctx = Context(0)
+    ctx.set_domain_periodic(1.0)
+    ctx.set_points(d["xyz0"])
+    x = ctx.lloyd(2)
+    assert np.abs(x - d["xyz2"]).max() < 1e-10
+
+
+# ---------------------------------------------------------------- cells vs oracles, fresh inputs
+@pytest.mark.parametrize("periodic", [False, True])
+def test_cells_vs_port_100k(Context, port, periodic):
+    """config 1 of BASELINE.json: 100K uniform seeds, volumes + centroids, one Lloyd step."""
+    xyz = oracles.uniform_seeds(100000, 12345)
+    R, ctx = run_cells(Context, xyz, None, periodic)
+    O = port.cells(xyz, periodic=periodic, k0=20)
+    assert (R.status == 0).all(), np.bincount(R.status)
+    check(R, O)
+    assert abs(R.m.sum() - 1.0) < SUM_TOL
+    x1 = ctx.lloyd(1)
+    x0 = port.lloyd_update(xyz, O.m, O.mg, periodic, 1.0)
+    assert np.abs(x1 - x0).max() < 1e-10
+
+
+def test_cells_vs_reference_live(Context, reference):
+    """Against the unmodified reference library where it travelled to this box."""
+    xyz = oracles.uniform_seeds(200000, 777)
+    R, ctx = run_cells(Context, xyz, None, True)
+    A = reference.cells_delaunay(xyz, periodic=True)
+    assert (R.status == 0).all()
+    check(R, A)
+    h = 200000 ** (-1.0 / 3.0)
+    w = 0.02 * h * h * np.random.default_rng(1).random(200000)
+    R, ctx = run_cells(Context, xyz, w, True)
+    A = reference.cells_delaunay(xyz, w=w, periodic=True)
+    assert A is not None and (R.status == 0).all()
+    check(R, A)
+
+
+def test_laguerre_large_weights_on_relaxed_seeds(Context, port):
+    """config 3 recipe: a few Lloyd iterations, then a = 0.25."""
+    n = 20000
+    xyz = oracles.uniform_seeds(n, 31)
+    ctx = Context(0)
+    ctx.set_domain_periodic(1.0)
+    ctx.set_points(xyz)
+    x = ctx.lloyd(5)
+    h = n ** (-1.0 / 3.0)
+    w = 0.25 * h * h * np.random.default_rng(2).random(n)
+    R, ctx = run_cells(Context, x, w, True)
+    O = port.cells(x, w=w, periodic=True)
+    assert ((R.status & ~np.uint8(4)) == 0).all()
+    check(R, O)
+    assert abs(R.m.sum() - 1.0) < SUM_TOL
+
+
+# ---------------------------------------------------------------- properties at size
+def test_volume_conservation_2m(Context):
+    n = 2000000
+    xyz = oracles.uniform_seeds(n, 2024)
+    ctx = Context(0)
+    ctx.set_domain_periodic(1.0)
+    ctx.set_points(xyz)
+    ctx.compute_cells()
+    m, mg, st = ctx.get_cells()
+    assert (st == 0).all(), np.bincount(st)
+    assert abs(m.sum() - 1.0) < SUM_TOL
+    assert (m > 0).all()
+    # centroids lie within one cell radius of their seed
+    c = mg / m[:, None]
+    assert np.abs(c - xyz).max() < 6.0 * n ** (-1.0 / 3.0)
+    # determinism: bitwise identical on a second run
+    ctx.compute_cells()
+    m2, mg2, st2 = ctx.get_cells()
+    assert (m == m2).all() and (mg == mg2).all()
+    # Lloyd decreases the CVT energy proxy: cells become more regular (variance of volumes drops)
+    ctx.lloyd(3)
+    ctx.compute_cells()
+    m3, _, st3 = ctx.get_cells()
+    assert (st3 == 0).all() and abs(m3.sum() - 1.0) < SUM_TOL
+    assert m3.std() < 0.7 * m.std()
+
+
+# ---------------------------------------------------------------- edge cases
+def test_edge_cases(Context, port):
+    from geogram_b200 import B200VorError
+    ctx = Context(0)
+    xyz = np.array([[0.25, 0.5, 0.5], [0.75, 0.5, 0.5]])
+    ctx.set_points(xyz)
+    ctx.compute_cells(want_faces=True)
+    R = GpuCells(ctx)
+    assert np.allclose(R.m, [0.5, 0.5]) and (R.status == 0).all()
+    assert list(R.face_nbr[0, : R.nfaces[0]]) == [1, oracles.BOX_ID, oracles.BOX_ID + 2,
+                                                  oracles.BOX_ID + 3, oracles.BOX_ID + 4,
+                                                  oracles.BOX_ID + 5]
+    # single point: the whole box
+    ctx.set_points(np.array([[0.3, 0.3, 0.3]]))
+    ctx.compute_cells()
+    m, mg, st = ctx.get_cells()
+    assert abs(m[0] - 1.0) < 1e-15 and st[0] == 0 and np.allclose(mg[0], 0.5)
+    # empty Laguerre cell
+    xyz = np.array([[0.5, 0.5, 0.5], [0.52, 0.5, 0.5], [0.2, 0.2, 0.2]])
+    ctx.set_points(xyz, np.array([0.0, 0.2, 0.0]))
+    ctx.compute_cells()
+    m, mg, st = ctx.get_cells()
+    assert m[0] == 0.0 and (st[0] & 4) and abs(m.sum() - 1.0) < 1e-12
+    # exact duplicates: the lower index keeps the cell (delaunay_nn.cpp:122-135)
+    xyz = oracles.uniform_seeds(500, 9)
+    xyz = np.concatenate([xyz, xyz[:20]])
+    ctx.set_points(xyz)
+    ctx.compute_cells()
+    m, mg, st = ctx.get_cells()
+    assert (st[500:] & 32).all() and (m[500:] == 0).all() and (st[:500] == 0).all()
+    assert abs(m.sum() - 1.0) < 1e-12
+    # bad arguments fail loudly
+    with pytest.raises(B200VorError):
+        ctx.set_points(np.zeros((0, 3)))
+    with pytest.raises(B200VorError):
+        Context(0).compute_cells()
+
+
+def test_degenerate_lattice_is_flagged_not_wrong(Context):
+    """Cospherical input: sign tests are exact ties.  The cell must either be right or be
+    flagged UNCERTAIN/DEGENERATE; never silently wrong, never a crash."""
+    g = 12
+    ax = (np.arange(g) + 0.5) / g
+    xyz = np.stack(np.meshgrid(ax, ax, ax, indexing="ij"), -1).reshape(-1, 3).copy()
+    for periodic in (False, True):
+        ctx = Context(0)
+        if periodic:
+            ctx.set_domain_periodic(1.0)
+        ctx.set_points(xyz)
+        ctx.compute_cells()
+        m, mg, st = ctx.get_cells()
+        clean = st == 0
+        assert np.allclose(m[clean], 1.0 / g ** 3, rtol=1e-9)
+        assert ((st & ~np.uint8(2 | 64)) == 0).all()
+        # ties do not change volumes: even flagged cells are cubes up to rounding
+        assert abs(m.sum() - 1.0) < 1e-6

@@ -1,0 +1,121 @@
+"""CPU tests: the restatement oracle (oracle/voro_oracle.cpp) against golden vectors
+generated from the unmodified reference (tests/golden/make_golden.py), and against the
+reference itself where oracle/_ref/libgeoref.so exists."""
+import numpy as np
+import pytest
+
+import oracles
+from conftest import Golden
+
+VOL_RTOL = 1e-9   # port vs reference: same algorithm, different summation order
+
+
+def check_cells(R, G, certified_only=False):
+    ok = np.ones(G.n, bool)
+    if certified_only:
+        ok = (R.flags & 1) == 0
+    bad = oracles.face_mismatches(R, G) if not certified_only else int(sum(
+        (R.nfaces[i] != G.nfaces[i]) or (R.faces(i) != G.face_nbr[i, : G.nfaces[i]]).any()
+        for i in np.nonzero(ok)[0]))
+    assert bad == 0
+    assert np.all(np.abs(R.m[ok] - G.m[ok]) <= VOL_RTOL * G.m[ok])
+    scale = np.cbrt(G.m[ok])[:, None] * G.m[ok][:, None]
+    assert np.all(np.abs(R.mg[ok] - G.mg[ok]) <= 1e-8 * scale + 1e-18)
+    return ok
+
+
+def test_knn_golden(port):
+    d = np.load(oracles.ROOT + "/tests/golden/knn_uniform_3000.npz")
+    nbr, d2 = port.knn(d["xyz"], 21)
+    assert (d2 == d["d2"]).all()          # bit-exact (test_nn_search/main.cpp:169-181)
+    assert (nbr == d["nbr"]).all()
+    nbq, d2q = port.knn(d["xyz"], 9, queries=d["q"])
+    assert (d2q == d["d2_q"]).all()
+    assert (nbq == d["nbr_q"]).all()
+
+
+def test_cells_box_golden(port):
+    G = Golden("cells_box_uniform_3000.npz")
+    R = port.cells(G.xyz, k0=20, areas=True)
+    check_cells(R, G)
+    assert (R.flags == 0).all()
+    assert abs(R.m.sum() - 1.0) < 1e-12
+    # same stopping rank and event counts as the reference's own SR loop (oracle B)
+    assert (R.kstop == G.extra["kstop_B"]).all()
+    assert (R.stats[:3] == G.extra["stats_B"][:3]).all()
+    nf = G.nfaces
+    col = np.arange(64)[None, :] < nf[:, None]
+    assert np.allclose(R.face_area[col], G.face_area[col], rtol=1e-7, atol=1e-14)
+
+
+def test_cells_periodic_golden(port):
+    G = Golden("cells_periodic_uniform_3000.npz")
+    R = port.cells(G.xyz, periodic=True)
+    check_cells(R, G)
+    assert (R.flags == 0).all()
+    assert abs(R.m.sum() - 1.0) < 1e-12
+
+
+@pytest.mark.parametrize("name,periodic", [("cells_periodic_laguerre_3000.npz", True),
+                                           ("cells_box_laguerre_3000.npz", False)])
+def test_cells_laguerre_golden(port, name, periodic):
+    G = Golden(name)
+    R = port.cells(G.xyz, w=G.w, periodic=periodic)
+    check_cells(R, G)
+    assert abs(R.m.sum() - 1.0) < 1e-12
+
+
+def test_cells_clustered_golden(port):
+    """kNN + security radius cannot certify fringe cells of clustered seeds:
+    they must be FLAGGED, and every certified cell must equal the exact oracle."""
+    G = Golden("cells_box_clustered_4000.npz")
+    R = port.cells(G.xyz, k0=20, kcap=400)
+    ok = check_cells(R, G, certified_only=True)
+    assert ok.sum() > 0.8 * G.n
+    R = port.cells(G.xyz, k0=20, kcap=3999)     # k may grow to n-1: everything certified
+    check_cells(R, G)
+    assert abs(R.m.sum() - 1.0) < 1e-12
+
+
+def test_lloyd_golden(port):
+    d = np.load(oracles.ROOT + "/tests/golden/lloyd2_periodic_3000.npz")
+    x = d["xyz0"]
+    for _ in range(2):
+        R = port.cells(x, periodic=True)
+        x = port.lloyd_update(x, R.m, R.mg, True, 1.0)
+    assert np.abs(x - d["xyz2"]).max() < 1e-11
+
+
+def test_edge_cases(port):
+    # two points: the bisector splits the box
+    xyz = np.array([[0.25, 0.5, 0.5], [0.75, 0.5, 0.5]])
+    R = port.cells(xyz, k0=20)
+    assert np.allclose(R.m, [0.5, 0.5])
+    assert np.allclose(R.mg / R.m[:, None], xyz)
+    assert list(R.faces(0)) == [1, oracles.BOX_ID, oracles.BOX_ID + 2, oracles.BOX_ID + 3,
+                                oracles.BOX_ID + 4, oracles.BOX_ID + 5]
+    # empty Laguerre cell: a point dominated by a heavy neighbour
+    xyz = np.array([[0.5, 0.5, 0.5], [0.52, 0.5, 0.5], [0.2, 0.2, 0.2]])
+    w = np.array([0.0, 0.2, 0.0])
+    R = port.cells(xyz, w=w)
+    assert R.m[0] == 0.0 and (R.flags[0] & 4)
+    assert abs(R.m.sum() - 1.0) < 1e-12
+
+
+def test_port_vs_reference_live(port, reference):
+    """Where the reference library is present: bigger, fresh inputs, both oracles."""
+    xyz = oracles.uniform_seeds(20000, 99)
+    nbr, d2 = port.knn(xyz, 33)
+    nbr_r, d2_r = reference.knn(xyz, 33)
+    assert (d2 == d2_r).all() and (nbr == nbr_r).all()
+    A = reference.cells_delaunay(xyz)
+    B = reference.cells_knn(xyz, k0=20)
+    R = port.cells(xyz, k0=20)
+    assert oracles.face_mismatches(R, A) == 0
+    assert oracles.face_mismatches(R, B) == 0
+    assert (R.kstop == B.kstop).all()
+    assert np.all(np.abs(R.m - A.m) <= VOL_RTOL * A.m)
+    Ap = reference.cells_delaunay(xyz, periodic=True)
+    Rp = port.cells(xyz, periodic=True)
+    assert oracles.face_mismatches(Rp, Ap) == 0
+    assert np.all(np.abs(Rp.m - Ap.m) <= VOL_RTOL * Ap.m)
