@@ -105,8 +105,8 @@ int cells_pipeline(Ctx* c, const b200vor_cell_params* params, bool collect_event
     if(p.kmax == 0) {
         p.kmax = 384;
     }
-    if(p.kmax > 570) {
-        p.kmax = 570;
+    if(p.kmax > 569) {
+        p.kmax = 569;   // row = k + 1 entries, kNN kernel capacity 570
     }
     if(c->n == 0) {
         set_error("b200vor_compute_cells: no points");
@@ -152,7 +152,7 @@ int cells_pipeline(Ctx* c, const b200vor_cell_params* params, bool collect_event
         }
         T.mark(2);
         CellJob cj = {nq, qlist, nullptr, 2, rl, c->knn.p, c->knn_flag.p, int(p.want_faces),
-                      collect_events ? 1 : 0, int(p.mode)};
+                      collect_events ? 1 : 0, int(p.mode), uint64_t(rl) >= ntotal ? 1 : 0};
         if((rc = run_cells(c, cj))) {
             return rc;
         }

@@ -93,6 +93,7 @@ template <int S> struct WarpCell {
     double X[S], Y[S], Z[S], W[S];
     float ea[S], eb[S], r2[S];
     uint32_t tri[S], adj[S];
+    bool degenerate;
     // warp-uniform
     uint32_t vmask[S];
     unsigned long long live;
@@ -136,6 +137,9 @@ template <int S> struct WarpCell {
         const float e48 = float(48.0 * kEps) * 1.001f, e4 = float(4.0 * kEps) * 1.001f;
         ea[s] = (e48 * Q + e4 * sx) * 1.001f;
         eb[s] = (e48 * (n0 * n1 * n2) + e4 * sw) * 1.001f;
+        if(!(sw > 2.0f * e48 * (n0 * n1 * n2))) {
+            degenerate = true;   // three (nearly) linearly dependent normals: no reliable vertex
+        }
         // |v|^2 rounded up (only the security radius uses it; 4.1 vs 4 leaves 2.5% slack)
         float num = __double2float_ru(x * x + y * y + z * z);
         float den = __double2float_rd(w * w);
@@ -151,6 +155,7 @@ template <int S> struct WarpCell {
             tri[s] = adj[s] = 0;
             vmask[s] = 0;
         }
+        degenerate = false;
         if(lane < 6) {
             int axis = lane >> 1;
             bool upper = lane & 1;
@@ -229,9 +234,13 @@ template <int S> struct WarpCell {
         for(int s = 0; s < S; ++s) {
             bool valid = (vmask[s] >> lane) & 1u;
             double dot = fma(a, X[s], fma(b, Y[s], fma(c, Z[s], d * W[s])));
-            cf[s] = valid && (dot < 0.0);
+            // conflict only when CERTAINLY outside: a tie (|dot| inside the error bound)
+            // leaves the vertex alone, like the reference's fast mode where ties are not
+            // conflicts (convex_cell.cpp:968); the cell is flagged UNCERTAIN
             float E = fmaf(nmaxf, ea[s], dabs * eb[s]);
-            unc |= valid && (__double2float_rd(fabs(dot)) <= E);
+            bool tie = __double2float_rd(fabs(dot)) <= E;
+            cf[s] = valid && !tie && (dot < 0.0);
+            unc |= valid && tie;
             cm[s] = __ballot_sync(kFull, cf[s]);
             any |= cm[s];
             nC += __popc(vmask[s]);
@@ -551,7 +560,7 @@ __device__ inline bool consistent(WarpCell<S>& C) {
             }
         }
     }
-    ok = __all_sync(kFull, ok);
+    ok = __all_sync(kFull, ok && !C.degenerate);
     __syncwarp();
     return ok && (T + 4 == 2 * F);
 }
@@ -657,6 +666,9 @@ __global__ void __launch_bounds__(32 * WPB) cells_knn_kernel(CellParams P) {
         }
     }
     C.status |= extra;
+    if(P.job.all_offered) {
+        certified = true;    // the table row holds every other seed
+    }
     if(P.job.knn_flag && P.job.knn_flag[trow]) {
         certified = false;
     }

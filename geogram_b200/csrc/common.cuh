@@ -162,6 +162,7 @@ struct CellJob {
     int want_faces;
     int collect_events;
     int mode;
+    int all_offered;         // 1: every row lists all other seeds (k >= n-1)
 };
 int run_cells(Ctx* c, const CellJob& job);
 int compact_failed(Ctx* c, const uint32_t* qlist_in, uint32_t nq_in, uint32_t* qlist_out,

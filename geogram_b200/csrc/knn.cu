@@ -32,14 +32,23 @@ struct KnnParams {
     KnnJob job;
 };
 
-__device__ inline bool key_less(double da, uint32_t ia, double db, uint32_t ib) {
-    return da < db || (da == db && ia < ib);
+// exact ties are ordered by USER index (grid order inside a cell depends on atomics, the
+// user index does not): results are deterministic run to run
+__device__ inline uint32_t user_id(const uint32_t* perm, uint32_t n, uint32_t id) {
+    uint32_t inst = id / n;
+    return __ldg(perm + (id - inst * n)) + inst * n;
 }
 
 template <int kStride> struct Heap {
     double* d;      // d[e * kStride]
     uint32_t* id;   // id[e * kStride]
     uint32_t count, k;
+    const uint32_t* perm;
+    uint32_t n;
+
+    __device__ inline bool key_less(double da, uint32_t ia, double db, uint32_t ib) const {
+        return da < db || (da == db && user_id(perm, n, ia) < user_id(perm, n, ib));
+    }
 
     __device__ inline void sift_down(uint32_t e, uint32_t len, double dv, uint32_t iv) {
         for(;;) {
@@ -167,6 +176,8 @@ __global__ void __launch_bounds__(kBlock) knn_kernel(KnnParams P) {
     H.id = hi + threadIdx.x;
     H.count = 0;
     H.k = k;
+    H.perm = P.perm;
+    H.n = P.n;
     bool complete = true;
     const uint32_t want_all = min(k, P.G.periodic ? 27u * P.n : P.n);
     uint32_t row = 0xFFFFFFFFu;

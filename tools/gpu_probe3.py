@@ -15,3 +15,5 @@ for periodic in (0, 1):
     ctx.set_points(xyz); ctx.compute_cells(want_faces=True)
     m, mg, st = ctx.get_cells(); nf, fn, fa = ctx.get_faces()
     print("lattice periodic=%d" % periodic, "sum-1 = %.3e" % (m.sum() - 1), "status", np.bincount(st).nonzero()[0], np.bincount(st)[np.bincount(st) > 0], "nf hist", np.bincount(nf))
+    bad = (st & ~np.uint8(66)) != 0
+    print("  other flags:", np.bincount(st[bad]) .nonzero()[0], "n=", bad.sum(), ctx.stats())
