@@ -28,7 +28,7 @@ EXPORTS = [
     "b200vor_set_domain_box", "b200vor_set_domain_periodic", "b200vor_set_points",
     "b200vor_knn", "b200vor_knn_points", "b200vor_compute_cells", "b200vor_get_cells",
     "b200vor_get_faces", "b200vor_lloyd", "b200vor_get_stats",
-    "b200vor_set_points_per_cell",
+    "b200vor_set_points_per_cell", "b200vor_set_stream", "b200vor_set_query_range",
 ]
 
 
@@ -94,6 +94,8 @@ def load_library():
     lib.b200vor_lloyd.argtypes = [vp, u32, ctypes.POINTER(CellParams), vp, i32]
     lib.b200vor_get_stats.argtypes = [vp, ctypes.POINTER(Stats)]
     lib.b200vor_set_points_per_cell.argtypes = [vp, dbl]
+    lib.b200vor_set_stream.argtypes = [vp, vp]
+    lib.b200vor_set_query_range.argtypes = [vp, u32, u32]
     _lib = lib
     return lib
 
@@ -141,6 +143,13 @@ class Context(object):
 
     def set_domain_periodic(self, period=1.0):
         self._check(self.lib.b200vor_set_domain_periodic(self.h, float(period)))
+
+    def set_stream(self, cuda_stream):
+        """cuda_stream: integer cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream)"""
+        self._check(self.lib.b200vor_set_stream(self.h, ctypes.c_void_p(int(cuda_stream))))
+
+    def set_query_range(self, first, last):
+        self._check(self.lib.b200vor_set_query_range(self.h, int(first), int(last)))
 
     def set_points_per_cell(self, ppc):
         self._check(self.lib.b200vor_set_points_per_cell(self.h, float(ppc)))
@@ -199,9 +208,11 @@ class Context(object):
         self._check(self.lib.b200vor_get_faces(self.h, _ptr(nf), _ptr(nbr), _ptr(area), FCAP, 0))
         return nf, nbr, area
 
-    def lloyd(self, iters, k0=0, kmax=0, mode=0, want_xyz=True):
+    def lloyd(self, iters, k0=0, kmax=0, mode=0, want_xyz=True, out=None):
+        """out: optional preallocated (n,3) float64 host array (e.g. pinned) for the result"""
         p = CellParams(int(k0), int(kmax), 0, int(mode))
-        out = np.zeros((self.n, 3)) if want_xyz else None
+        if out is None:
+            out = np.zeros((self.n, 3)) if want_xyz else None
         self._check(self.lib.b200vor_lloyd(self.h, int(iters), ctypes.byref(p), _ptr(out), 0))
         return out
 

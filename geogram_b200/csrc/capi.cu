@@ -137,6 +137,18 @@ int cells_pipeline(Ctx* c, const b200vor_cell_params* params, bool collect_event
     uint32_t k = std::min(p.k0, p.kmax);
     uint32_t nq = n;
     const uint32_t* qlist = nullptr;
+    if(c->q0 > 0 || c->q1 < n) {
+        // sharded run: only the cells of the seeds with user index in [q0, q1)
+        if((rc = c->qlist.reserve(n)) || (rc = c->qlist2.reserve(n)) ||
+           (rc = select_range(c, c->qlist2.p, &nq))) {
+            return rc;
+        }
+        qlist = c->qlist2.p;
+        B200_CUDA_CHECK(cudaMemsetAsync(c->status.p, 0, n, c->stream));
+        if(collect_events) {
+            B200_CUDA_CHECK(cudaMemsetAsync(c->evcount.p, 0, 2 * size_t(n) * sizeof(uint32_t), c->stream));
+        }
+    }
     c->stats.passes = 0;
     memset(c->stats.n_pass, 0, sizeof(c->stats.n_pass));
     memset(c->stats.k_pass, 0, sizeof(c->stats.k_pass));
@@ -216,6 +228,7 @@ int ensure_grid(Ctx* c) {
     T.mark(0);
     B200_CUDA_CHECK(cudaStreamSynchronize(c->stream));
     c->stats.ms_grid += T.sum(1);
+    c->grid_dirty = false;
     return B200VOR_OK;
 }
 
@@ -255,6 +268,7 @@ int b200vor_create(b200vor_ctx** out, int device) {
     b200vor_ctx* h = new b200vor_ctx();
     h->c.device = device;
     B200_CUDA_CHECK(cudaStreamCreateWithFlags(&h->c.stream, cudaStreamNonBlocking));
+    h->c.own_stream = true;
     *out = h;
     return B200VOR_OK;
 }
@@ -272,7 +286,9 @@ void b200vor_destroy(b200vor_ctx* h) {
     c.counter.release(); c.m.release(); c.mg.release(); c.status.release();
     c.nfaces.release(); c.face_nbr.release(); c.face_area.release(); c.evcount.release();
     c.sums.release(); c.out_nbr.release(); c.out_d2.release(); c.qpts.release();
-    cudaStreamDestroy(c.stream);
+    if(c.own_stream) {
+        cudaStreamDestroy(c.stream);
+    }
     delete h;
 }
 
@@ -300,6 +316,33 @@ int b200vor_set_domain_periodic(b200vor_ctx* h, double period) {
     }
     h->c.periodic = 1;
     h->c.period = period;
+    h->c.cells_valid = h->c.faces_valid = false;
+    return B200VOR_OK;
+}
+
+int b200vor_set_stream(b200vor_ctx* h, void* cuda_stream) {
+    if(!h) {
+        set_error("b200vor_set_stream: null context");
+        return B200VOR_ERR_ARG;
+    }
+    Ctx& c = h->c;
+    cudaSetDevice(c.device);
+    cudaStreamSynchronize(c.stream);
+    if(c.own_stream) {
+        cudaStreamDestroy(c.stream);
+    }
+    c.stream = static_cast<cudaStream_t>(cuda_stream);
+    c.own_stream = false;
+    return B200VOR_OK;
+}
+
+int b200vor_set_query_range(b200vor_ctx* h, uint32_t first, uint32_t last) {
+    if(!h || first > last) {
+        set_error("b200vor_set_query_range: invalid range");
+        return B200VOR_ERR_ARG;
+    }
+    h->c.q0 = first;
+    h->c.q1 = last;
     h->c.cells_valid = h->c.faces_valid = false;
     return B200VOR_OK;
 }
@@ -391,7 +434,10 @@ int b200vor_knn(b200vor_ctx* h, uint32_t k, uint32_t* nbr, double* d2, int on_de
         dn = c->out_nbr.p;
         dd = d2 ? c->out_d2.p : nullptr;
     }
-    // the public kNN ignores the periodic domain, like the reference's kd-tree
+    if(c->grid_dirty && (rc = ensure_grid(c))) {
+        return rc;
+    }
+    // the public kNN is not offered on a periodic domain (the reference's kd-tree has none)
     int saved = c->grid.periodic;
     if(saved) {
         set_error("b200vor_knn: not available on a periodic domain");
@@ -432,6 +478,9 @@ int b200vor_knn_points(b200vor_ctx* h, uint32_t nq, const double* q, uint32_t k,
     }
     B200_CUDA_CHECK(cudaSetDevice(c->device));
     int rc;
+    if(c->grid_dirty && (rc = ensure_grid(c))) {
+        return rc;
+    }
     uint32_t* dn = nbr;
     double* dd = d2;
     const double* dq = q;
@@ -467,8 +516,9 @@ int b200vor_compute_cells(b200vor_ctx* h, const b200vor_cell_params* params) {
     }
     Ctx* c = &h->c;
     B200_CUDA_CHECK(cudaSetDevice(c->device));
-    if(c->grid.periodic != c->periodic || (c->periodic && c->grid.period != c->period)) {
-        int rc = ensure_grid(c);   // the domain changed after set_points
+    if(c->grid_dirty || c->grid.periodic != c->periodic ||
+       (c->periodic && c->grid.period != c->period)) {
+        int rc = ensure_grid(c);   // points moved (Lloyd) or the domain changed after set_points
         if(rc) {
             return rc;
         }
@@ -538,21 +588,16 @@ int b200vor_lloyd(b200vor_ctx* h, uint32_t iters, const b200vor_cell_params* par
     int rc;
     c->stats.ms_knn = c->stats.ms_clip = 0.f;
     for(uint32_t it = 0; it < iters; ++it) {
-        if(it > 0) {
-            if((rc = ensure_grid(c))) {
-                return rc;
-            }
+        if(c->grid_dirty && (rc = ensure_grid(c))) {
+            return rc;
         }
         if((rc = cells_pipeline(c, &p, false)) || (rc = lloyd_update(c))) {
             return rc;
         }
+        c->grid_dirty = true;
     }
     if(iters > 0) {
-        // keep the context consistent with the relaxed points
-        if((rc = ensure_grid(c))) {
-            return rc;
-        }
-        c->cells_valid = c->faces_valid = false;
+        c->cells_valid = c->faces_valid = false;   // the grid is rebuilt lazily at the next use
     }
     if(xyz_out) {
         if((rc = copy_out(xyz_out, c->xyz.p, 3 * size_t(c->n) * sizeof(double), on_device, c->stream))) {

@@ -723,10 +723,46 @@ __global__ void compact_kernel(const uint32_t* __restrict__ qin, uint32_t nq,
     }
 }
 
-__global__ void lloyd_kernel(uint32_t n, double* __restrict__ xyz,
+// grid-order indices of the seeds whose USER index lies in [u0, u1) (multi-GPU shard)
+__global__ void select_range_kernel(uint32_t n, const uint32_t* __restrict__ perm, uint32_t u0,
+                                    uint32_t u1, uint32_t* __restrict__ qout,
+                                    uint32_t* __restrict__ counter) {
+    // one block-wide ordered compaction per 1024 seeds keeps the list in grid order
+    __shared__ uint32_t wcount[32];
+    __shared__ uint32_t base;
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool in = false;
+    if(i < n) {
+        uint32_t u = perm[i];
+        in = u >= u0 && u < u1;
+    }
+    uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    uint32_t bal = __ballot_sync(kFull, in);
+    if(lane == 0) {
+        wcount[wid] = __popc(bal);
+    }
+    __syncthreads();
+    if(threadIdx.x == 0) {
+        uint32_t tot = 0;
+        for(uint32_t w = 0; w < blockDim.x / 32; ++w) {
+            uint32_t cw = wcount[w];
+            wcount[w] = tot;
+            tot += cw;
+        }
+        // blocks append in arbitrary order; the per-block runs stay in grid order, and the
+        // result of every cell is independent of the list order
+        base = atomicAdd(counter, tot);
+    }
+    __syncthreads();
+    if(in) {
+        qout[base + wcount[wid] + __popc(bal & ((1u << lane) - 1u))] = i;
+    }
+}
+
+__global__ void lloyd_kernel(uint32_t n, uint32_t u0, double* __restrict__ xyz,
                              const double* __restrict__ m, const double* __restrict__ mg,
                              int periodic, double period) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t i = u0 + blockIdx.x * blockDim.x + threadIdx.x;
     if(i >= n) {
         return;
     }
@@ -843,9 +879,30 @@ int compact_failed(Ctx* c, const uint32_t* qlist_in, uint32_t nq_in, uint32_t* q
     return B200VOR_OK;
 }
 
+int select_range(Ctx* c, uint32_t* qout, uint32_t* count_out_host) {
+    int rc = c->counter.reserve(4);
+    if(rc) {
+        return rc;
+    }
+    B200_CUDA_CHECK(cudaMemsetAsync(c->counter.p, 0, sizeof(uint32_t), c->stream));
+    uint32_t nblk = (c->n + 1023) / 1024;
+    select_range_kernel<<<nblk, 1024, 0, c->stream>>>(c->n, c->perm.p, c->q0, c->q1, qout,
+                                                      c->counter.p);
+    c->stats.gpu_launches++;
+    B200_CUDA_CHECK(cudaMemcpyAsync(count_out_host, c->counter.p, sizeof(uint32_t),
+                                    cudaMemcpyDeviceToHost, c->stream));
+    B200_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return B200VOR_OK;
+}
+
 int lloyd_update(Ctx* c) {
-    uint32_t nblk = (c->n + 255) / 256;
-    lloyd_kernel<<<nblk, 256, 0, c->stream>>>(c->n, c->xyz.p, c->m.p, c->mg.p, c->periodic,
+    uint32_t u1 = c->q1 < c->n ? c->q1 : c->n;
+    uint32_t cnt = u1 > c->q0 ? u1 - c->q0 : 0;
+    if(cnt == 0) {
+        return B200VOR_OK;
+    }
+    uint32_t nblk = (cnt + 255) / 256;
+    lloyd_kernel<<<nblk, 256, 0, c->stream>>>(u1, c->q0, c->xyz.p, c->m.p, c->mg.p, c->periodic,
                                               c->period);
     c->stats.gpu_launches++;
     B200_CUDA_CHECK(cudaGetLastError());

@@ -105,6 +105,9 @@ struct Ctx {
     double ppc = 4.0;
 
     uint32_t n = 0;
+    uint32_t q0 = 0, q1 = 0xFFFFFFFFu;   // user-index range of the cells to compute
+    bool own_stream = true;
+    bool grid_dirty = true;
     bool has_w = false;
     double wmax = 0.0;
     DevBuf<double> xyz;        // user order, packed 3n
@@ -168,6 +171,7 @@ int run_cells(Ctx* c, const CellJob& job);
 int compact_failed(Ctx* c, const uint32_t* qlist_in, uint32_t nq_in, uint32_t* qlist_out,
                    uint32_t* rows_out, uint32_t* count_out_host, uint8_t mask);
 int lloyd_update(Ctx* c);
+int select_range(Ctx* c, uint32_t* qout, uint32_t* count_out_host);
 int reduce_events(Ctx* c);
 
 }  // namespace b200vor

@@ -127,6 +127,14 @@ int b200vor_get_faces(b200vor_ctx* ctx, uint32_t* nfaces, uint32_t* face_nbr,
 int b200vor_lloyd(b200vor_ctx* ctx, uint32_t iters, const b200vor_cell_params* params,
                   double* xyz_out, int on_device);
 
+/* ---- execution control ---- */
+/* run on the caller's CUDA stream (a cudaStream_t passed as void*; e.g. torch's current
+ * stream) instead of the context's own; the caller keeps ownership of the stream */
+int b200vor_set_stream(b200vor_ctx* ctx, void* cuda_stream);
+/* multi-GPU sharding: compute (and Lloyd-update) only the cells of the seeds whose index
+ * lies in [first, last); every rank still holds all seeds (default: all) */
+int b200vor_set_query_range(b200vor_ctx* ctx, uint32_t first, uint32_t last);
+
 /* ---- introspection ---- */
 int b200vor_get_stats(b200vor_ctx* ctx, b200vor_stats* stats);
 /* tuning knob: target points per grid cell (default 4.0); takes effect at the next set_points */
