@@ -152,7 +152,37 @@ int cells_pipeline(Ctx* c, const b200vor_cell_params* params, bool collect_event
     c->stats.passes = 0;
     memset(c->stats.n_pass, 0, sizeof(c->stats.n_pass));
     memset(c->stats.k_pass, 0, sizeof(c->stats.k_pass));
-    for(int pass = 0; pass < 8 && nq > 0; ++pass) {
+    int pass0 = 0;
+    if(p.mode != 2) {
+        // fused grid walk: one launch, no neighbour table (fused.cu)
+        T.mark(2);
+        if((rc = run_cells_fused(c, nq, qlist, int(p.want_faces), collect_events ? 1 : 0, 0.f))) {
+            return rc;
+        }
+        T.mark(0);
+        c->stats.n_pass[0] = nq;
+        c->stats.k_pass[0] = 0;
+        c->stats.passes = 1;
+        pass0 = 1;
+        if(p.mode == 1) {
+            nq = 0;
+        } else {
+            // the cells it could not finish inside its fixed capacities go through the
+            // kNN-table pipeline below
+            if((rc = c->qlist.reserve(nq)) || (rc = c->qlist2.reserve(nq))) {
+                return rc;
+            }
+            uint32_t* out = (qlist == c->qlist.p) ? c->qlist2.p : c->qlist.p;
+            uint32_t nfail = 0;
+            if((rc = compact_failed(c, qlist, nq, out, nullptr, &nfail,
+                                    B200VOR_CELL_UNCERTIFIED | B200VOR_CELL_OVERFLOW))) {
+                return rc;
+            }
+            qlist = out;
+            nq = nfail;
+        }
+    }
+    for(int pass = pass0; pass < 8 && nq > 0; ++pass) {
         uint32_t rl = row_len(k);
         if((rc = c->knn.reserve(size_t(nq) * rl)) || (rc = c->knn_flag.reserve(nq))) {
             return rc;

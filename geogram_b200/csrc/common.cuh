@@ -168,6 +168,9 @@ struct CellJob {
     int all_offered;         // 1: every row lists all other seeds (k >= n-1)
 };
 int run_cells(Ctx* c, const CellJob& job);
+// fused.cu
+int run_cells_fused(Ctx* c, uint32_t nq, const uint32_t* qlist, int want_faces,
+                    int collect_events, float target);
 int compact_failed(Ctx* c, const uint32_t* qlist_in, uint32_t nq_in, uint32_t* qlist_out,
                    uint32_t* rows_out, uint32_t* count_out_host, uint8_t mask);
 int lloyd_update(Ctx* c);

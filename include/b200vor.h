@@ -68,8 +68,10 @@ typedef struct b200vor_cell_params {
     uint32_t k0;          /* neighbours fetched in the first pass (0 = default 48)            */
     uint32_t kmax;        /* cap on k for the re-launches of uncertified cells (0 = 384)      */
     uint32_t want_faces;  /* 1: keep per-cell face lists (+ areas) for b200vor_get_faces      */
-    uint32_t mode;        /* 0 = kNN table -> clipper (re-launch failing cells with larger k)
-                             1 = fused grid walk (no kNN table)                               */
+    uint32_t mode;        /* 0 = fused grid walk (no kNN table); the cells it flags UNCERTIFIED /
+                                 OVERFLOW are re-done by the kNN-table pipeline
+                             1 = fused grid walk only (flags are left on the cells)
+                             2 = kNN table -> clipper (re-launch failing cells with larger k) */
 } b200vor_cell_params;
 
 typedef struct b200vor_stats {
