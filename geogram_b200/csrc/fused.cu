@@ -41,8 +41,8 @@ namespace b200vor {
 
 namespace {
 
-constexpr int NT = 64;      // cell-vertex (dual triangle) slots
-constexpr int PC = 64;      // plane slots (0..5 = clipping box)
+constexpr int NT = 48;      // cell-vertex (dual triangle) slots
+constexpr int PC = 56;      // plane slots (0..5 = clipping box)
 constexpr int POOL = 64;    // candidate pool
 constexpr int FC = 40;      // faces of a finished cell that the twin table can index
 constexpr int kMaxRing = 4;
@@ -91,6 +91,7 @@ template <int G> struct __align__(16) TeamShared {
     uint32_t gid[PC];        // grid-order index of the plane's neighbour seed
     float pnm[PC];           // max |normal component| of the plane, rounded up
     uint32_t cand_j[G];
+    float cand_m[G];         // max(|normal|max, |d|) of the staged plane, rounded up
     uint16_t rec[NT];        // border edges of a cut: a | b << 8
     uint8_t pool_img[POOL];
     uint8_t order[POOL];     // pool entries in ascending distance
@@ -151,6 +152,12 @@ template <int G> struct Team {
 };
 
 __device__ inline bool wany(bool p) { return __any_sync(kFull, p) != 0; }
+
+// translation (-period, 0, +period) of one axis of a packed periodic image (2 bits: 0,1,2)
+__device__ inline double img_shift(uint32_t code, double period) {
+    code &= 3u;
+    return code == 1u ? 0.0 : (code == 0u ? -period : period);
+}
 
 struct Plane {
     double a, b, c, d;
@@ -274,7 +281,7 @@ __device__ inline double coverage2(const GridDesc& Gd, double sx, double sy, dou
 }
 
 template <int G, bool FACES, int WPB>
-__global__ void __launch_bounds__(32 * WPB) cells_fused_kernel(FusedParams P) {
+__global__ void __launch_bounds__(32 * WPB, 4) cells_fused_kernel(FusedParams P) {
     constexpr int TPW = 32 / G;
     constexpr int R = NT / G;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -356,6 +363,18 @@ __global__ void __launch_bounds__(32 * WPB) cells_fused_kernel(FusedParams P) {
     bool first = true, retry = false;
     int shrink = 0;
     uint32_t cnt = 0, pos = 0;
+    // d2 beyond which no bisector can cut the cell (generic_RVD.h:2322; Laguerre: a power
+    // plane cuts only if |q| <= R + sqrt(R^2 + wmax - wi))
+    auto sr_bound = [&](float r2) -> double {
+        double b = 4.1 * double(r2);
+        if(P.has_w) {
+            double Rr = sqrt(double(r2));
+            double sr = Rr + sqrt(double(r2) + dw);
+            b = 1.025 * sr * sr;
+        }
+        return b;
+    };
+    double bnd = sr_bound(R2);
 
     while(wany(!done)) {
         // ---- next distance shell [lo,hi) for the teams whose pool is used up ----
@@ -371,14 +390,7 @@ __global__ void __launch_bounds__(32 * WPB) cells_fused_kernel(FusedParams P) {
             } else {
                 lo = hi;
                 for(;;) {
-                    // d2 beyond which no bisector can cut the cell (generic_RVD.h:2322;
-                    // Laguerre: a power plane cuts only if |q| <= R + sqrt(R^2 + wmax - wi))
-                    double bound = 4.1 * double(R2);
-                    if(P.has_w) {
-                        double Rr = sqrt(double(R2));
-                        double sr = Rr + sqrt(double(R2) + dw);
-                        bound = 1.025 * sr * sr;
-                    }
+                    const double bound = bnd;
                     if(lo > bound) {
                         certified = true;
                         done = true;
@@ -497,11 +509,9 @@ __global__ void __launch_bounds__(32 * WPB) cells_fused_kernel(FusedParams P) {
                             im = (dimg & 0x3Cu) | ((dimg >> 8) & 3u);
                         }
                         Seed sj = load_seed(P.sorted + j);
-                        double tx = double(int(im & 3u) - 1), ty = double(int((im >> 2) & 3u) - 1),
-                               tz = double(int((im >> 4) & 3u) - 1);
-                        double qx = (sj.x + tx * P.period) - si.x;
-                        double qy = (sj.y + ty * P.period) - si.y;
-                        double qz = (sj.z + tz * P.period) - si.z;
+                        double qx = (sj.x + img_shift(im, P.period)) - si.x;
+                        double qy = (sj.y + img_shift(im >> 2, P.period)) - si.y;
+                        double qz = (sj.z + img_shift(im >> 4, P.period)) - si.z;
                         d2 = qx * qx + qy * qy + qz * qz;
                         in = d2 >= lo && d2 < hi && !(j == i && im == kImg0);
                     }
@@ -533,14 +543,15 @@ __global__ void __launch_bounds__(32 * WPB) cells_fused_kernel(FusedParams P) {
             }
             // ================================================================ sort
             const bool so = sc && !retry;
-            uint32_t key[R];
+            constexpr int RP = POOL / G;
+            uint32_t key[RP];
 #pragma unroll
-            for(int r = 0; r < R; ++r) {
+            for(int r = 0; r < RP; ++r) {
                 uint32_t e = lt + G * r;
                 key[r] = (so && e < cnt) ? sh->pool_key[e] : 0xffffffffu;
             }
             if(wany(so && cnt > uint32_t(G))) {
-                bitonic_sort<G, R>(lt, key);
+                bitonic_sort<G, RP>(lt, key);
             } else {
                 uint32_t k1[1] = {key[0]};
                 bitonic_sort<G, 1>(lt, k1);
@@ -548,7 +559,7 @@ __global__ void __launch_bounds__(32 * WPB) cells_fused_kernel(FusedParams P) {
             }
             if(so) {
 #pragma unroll
-                for(int r = 0; r < R; ++r) {
+                for(int r = 0; r < RP; ++r) {
                     uint32_t e = lt + G * r;
                     if(e < cnt) {
                         sh->order[e] = uint8_t(key[r] & 63u);
@@ -568,121 +579,113 @@ __global__ void __launch_bounds__(32 * WPB) cells_fused_kernel(FusedParams P) {
                 uint32_t j = sh->pool_j[idx];
                 uint32_t im = sh->pool_img[idx];
                 Seed sj = load_seed(P.sorted + j);
-                double tx = double(int(im & 3u) - 1), ty = double(int((im >> 2) & 3u) - 1),
-                       tz = double(int((im >> 4) & 3u) - 1);
-                double qx = (sj.x + tx * P.period) - si.x;
-                double qy = (sj.y + ty * P.period) - si.y;
-                double qz = (sj.z + tz * P.period) - si.z;
+                double qx = (sj.x + img_shift(im, P.period)) - si.x;
+                double qy = (sj.y + img_shift(im >> 2, P.period)) - si.y;
+                double qz = (sj.z + img_shift(im >> 4, P.period)) - si.z;
                 double d2 = qx * qx + qy * qy + qz * qz;
                 // plane (i,j) = (-2q, |q|^2 + wi - wj) (periodic_delaunay_3d.cpp:3719-3726,
                 // seed-centred frame)
                 double2* cp = reinterpret_cast<double2*>(sh->cand[lt]);
+                const double pd = d2 + (si.w - sj.w);
                 cp[0] = make_double2(-2.0 * qx, -2.0 * qy);
-                cp[1] = make_double2(-2.0 * qz, d2 + (si.w - sj.w));
+                cp[1] = make_double2(-2.0 * qz, pd);
+                sh->cand_m[lt] = __double2float_ru(
+                    fmax(fmax(2.0 * fabs(qx), 2.0 * fabs(qy)), fmax(2.0 * fabs(qz), fabs(pd))));
                 sh->cand_d2[lt] = d2;
                 sh->cand_j[lt] = j;
                 sh->cand_img[lt] = uint8_t(im);
             }
             __syncwarp();
-            while(wany(A && !done && pos < bend)) {
+            for(;;) {
                 // ---- search: each team advances to its next plane that cuts ----
                 bool found = false;
-                Plane pe;
-                pe.a = pe.b = pe.c = pe.d = 0.0;
-                uint32_t gj = 0, gi = 0;
-                uint32_t cm[R];
-                uint32_t cfbits = 0, nconf = 0;
-#pragma unroll
-                for(int r = 0; r < R; ++r) {
-                    cm[r] = 0;
-                }
-                while(wany(A && !done && !found && pos < bend)) {
+                uint32_t fk = 0;
+                for(;;) {
                     bool Q = A && !done && !found && pos < bend;
+                    if(!wany(Q)) {
+                        break;
+                    }
                     const uint32_t k = Q ? pos - b0 : 0u;
                     if(Q) {
                         double d2t = sh->cand_d2[k];
-                        gj = sh->cand_j[k];
-                        gi = sh->cand_img[k];
                         if(d2t == 0.0) {
                             // exact duplicate (delaunay_nn.cpp:122-135): the lower user
                             // index keeps the cell
-                            if(gi == kImg0 && __ldg(P.perm + gj) < row) {
+                            if(sh->cand_img[k] == kImg0 && __ldg(P.perm + sh->cand_j[k]) < row) {
                                 extra |= B200VOR_CELL_DUPLICATE;
                             }
                             ++pos;
                             Q = false;
-                        } else {
-                            double bnd = 4.1 * double(R2);
-                            if(P.has_w) {
-                                double Rr = sqrt(double(R2));
-                                double sr = Rr + sqrt(double(R2) + dw);
-                                bnd = 1.025 * sr * sr;
-                            }
-                            if(d2t > bnd) {
-                                certified = true;   // security radius reached
-                                done = true;
-                                Q = false;
-                            }
+                        } else if(d2t > bnd) {
+                            certified = true;   // security radius reached
+                            done = true;
+                            Q = false;
                         }
                     }
                     // ---- sign tests of the plane against the cell vertices ----
-                    Plane pq = load_plane(sh->cand[k]);
-                    const float nmaxf = __double2float_ru(fmax(fabs(pq.a), fmax(fabs(pq.b), fabs(pq.c))));
-                    const float dabs = __double2float_ru(fabs(pq.d));
-                    const float M = fmaxf(nmaxf, dabs) * 1.0001f;
-                    uint32_t tcm[R];
-                    uint32_t tcf = 0, tn = 0;
-                    bool unc = false;
+                    const Plane pq = load_plane(sh->cand[k]);
+                    const float M = sh->cand_m[k] * 1.0001f;
+                    bool cfany = false, unc = false;
 #pragma unroll
                     for(int r = 0; r < R; ++r) {
-                        tcm[r] = 0;
-                        if(wany(Q && uint32_t(G * r) < T)) {
-                            uint32_t s = lt + G * r;
-                            bool cf = false;
-                            if(Q && s < T) {
-                                const double2* p = reinterpret_cast<const double2*>(sh->vx[s]);
-                                double2 xy = p[0], zw = p[1];
-                                double dot = fma(pq.a, xy.x, fma(pq.b, xy.y, fma(pq.c, zw.x, pq.d * zw.y)));
-                                float E = M * sh->ve[s];
-                                // conflict only when CERTAINLY outside; a tie leaves the
-                                // vertex alone (reference fast mode, convex_cell.cpp:968)
-                                // and flags the cell
-                                bool tie = __double2float_rd(fabs(dot)) <= E;
-                                cf = !tie && (dot < 0.0);
-                                unc |= tie;
-                            }
-                            tcm[r] = tm.ballot(cf);
-                            tcf |= cf ? (1u << r) : 0u;
-                            tn += __popc(tcm[r]);
+                        uint32_t s = lt + G * r;
+                        if(Q && s < T) {
+                            const double2* p = reinterpret_cast<const double2*>(sh->vx[s]);
+                            double2 xy = p[0], zw = p[1];
+                            double dot = fma(pq.a, xy.x, fma(pq.b, xy.y, fma(pq.c, zw.x, pq.d * zw.y)));
+                            float E = M * sh->ve[s];
+                            // conflict only when CERTAINLY outside; a tie leaves the vertex
+                            // alone (reference fast mode, convex_cell.cpp:968) and flags
+                            // the cell
+                            bool tie = __double2float_rd(fabs(dot)) <= E;
+                            cfany |= !tie && (dot < 0.0);
+                            unc |= tie;
                         }
                     }
-                    const bool tunc = tm.any(unc);
+                    const uint32_t bc = __ballot_sync(kFull, cfany), bu = __ballot_sync(kFull, unc);
                     if(Q) {
                         ++nP;
                         nC += T;
-                        if(tunc) {
+                        if((bu >> tm.tbase) & Team<G>::kGMask) {
                             status |= B200VOR_CELL_UNCERTAIN;
                         }
-                        if(tn == 0) {
-                            ++pos;
-                        } else {
+                        if((bc >> tm.tbase) & Team<G>::kGMask) {
                             found = true;
-                            pe = pq;
-                            nconf = tn;
-                            cfbits = tcf;
-#pragma unroll
-                            for(int r = 0; r < R; ++r) {
-                                cm[r] = tcm[r];
-                            }
+                            fk = k;
+                        } else {
+                            ++pos;
                         }
                     }
                 }
                 if(!wany(found)) {
-                    continue;
+                    break;
                 }
                 // ================================================================ cut
                 // (triangulate_conflict_zone, convex_cell.cpp:761-865, without adjacency)
                 bool F = found;
+                const Plane pe = load_plane(sh->cand[fk]);
+                const uint32_t gj = sh->cand_j[fk], gi = sh->cand_img[fk];
+                uint32_t cm[R];
+                uint32_t cfbits = 0, nconf = 0;
+                {
+                    const float M = sh->cand_m[fk] * 1.0001f;
+#pragma unroll
+                    for(int r = 0; r < R; ++r) {
+                        uint32_t s = lt + G * r;
+                        bool cf = false;
+                        if(F && s < T) {
+                            const double2* p = reinterpret_cast<const double2*>(sh->vx[s]);
+                            double2 xy = p[0], zw = p[1];
+                            double dot = fma(pe.a, xy.x, fma(pe.b, xy.y, fma(pe.c, zw.x, pe.d * zw.y)));
+                            float E = M * sh->ve[s];
+                            bool tie = __double2float_rd(fabs(dot)) <= E;
+                            cf = !tie && (dot < 0.0);
+                        }
+                        cm[r] = tm.ballot(cf);
+                        cfbits |= cf ? (1u << r) : 0u;
+                        nconf += __popc(cm[r]);
+                    }
+                }
                 if(F) {
                     ++pos;
                     if(nconf == T) {
@@ -791,12 +794,13 @@ __global__ void __launch_bounds__(32 * WPB) cells_fused_kernel(FusedParams P) {
                 if(F) {
                     live |= 1ull << pn;
                     if(lt == 0) {
+                        const float npn_pl = __double2float_ru(fmax(fabs(pe.a), fmax(fabs(pe.b), fabs(pe.c))));
                         double2* p = reinterpret_cast<double2*>(sh->pl[pn]);
                         p[0] = make_double2(pe.a, pe.b);
                         p[1] = make_double2(pe.c, pe.d);
                         sh->gid[pn] = gj;
                         sh->gimg[pn] = uint8_t(gi);
-                        sh->pnm[pn] = __double2float_ru(fmax(fabs(pe.a), fmax(fabs(pe.b), fabs(pe.c))));
+                        sh->pnm[pn] = npn_pl;
                     }
                 }
                 // ---- fewer new vertices than holes (two faces vanished at once): the
@@ -841,13 +845,13 @@ __global__ void __launch_bounds__(32 * WPB) cells_fused_kernel(FusedParams P) {
                     }
                 }
                 // ---- one new vertex per border edge ----
+                const float npn = __double2float_ru(fmax(fabs(pe.a), fmax(fabs(pe.b), fabs(pe.c))));
                 for(uint32_t k0 = 0; wany(F && k0 < nnew); k0 += G) {
                     uint32_t kk = k0 + lt;
                     if(F && kk < nnew) {
                         uint32_t rr = sh->rec[kk];
                         uint32_t u = rr & 0xffu, v = rr >> 8;
                         uint32_t s = kk < nconf ? uint32_t(sh->cslot[kk]) : T + (kk - nconf);
-                        float npn = __double2float_ru(fmax(fabs(pe.a), fmax(fabs(pe.b), fabs(pe.c))));
                         Vertex V = make_vertex(pe, load_plane(sh->pl[u]), load_plane(sh->pl[v]), npn,
                                                sh->pnm[u], sh->pnm[v]);
                         degenerate |= V.degenerate;
@@ -872,6 +876,7 @@ __global__ void __launch_bounds__(32 * WPB) cells_fused_kernel(FusedParams P) {
                     rb = tm.max_u32(rb);
                     if(F) {
                         R2 = __uint_as_float(rb);
+                        bnd = sr_bound(R2);
                     }
                 }
             }
