@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libb200vor.so")
+LIB_PATH = os.environ.get("B200VOR_LIB") or os.path.join(_HERE, "lib", "libb200vor.so")
 
 BOX_ID = 0xFFFFFFF0
 CELL_OK = 0

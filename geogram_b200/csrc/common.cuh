@@ -102,7 +102,7 @@ struct Ctx {
     int periodic = 0;
     double period = 1.0;
     double box[6] = {0, 0, 0, 1, 1, 1};
-    double ppc = 4.0;
+    double ppc = 8.0;
 
     uint32_t n = 0;
     uint32_t q0 = 0, q1 = 0xFFFFFFFFu;   // user-index range of the cells to compute

@@ -37,18 +37,24 @@
 //    kNN-table pipeline (capi.cu), never silently accepted.
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace b200vor {
 
 namespace {
 
+#ifndef B200VOR_FUSED_MINBLOCKS
+#define B200VOR_FUSED_MINBLOCKS 4
+#endif
 constexpr int NT = 48;      // cell-vertex (dual triangle) slots
-constexpr int PC = 56;      // plane slots (0..5 = clipping box)
+constexpr int PC = 40;      // plane slots (0..5 = clipping box)
 constexpr int POOL = 64;    // candidate pool
 constexpr int FC = 40;      // faces of a finished cell that the twin table can index
 constexpr int kMaxRing = 4;
 constexpr double kEps = 1.1102230246251565e-16;   // 2^-53
 constexpr uint32_t kImg0 = 1u | (1u << 2) | (1u << 4);   // packed zero translation
 constexpr uint32_t kImgBox = 0xFFu;
+constexpr unsigned long long kLiveInit = 0x3Full | ~((1ull << PC) - 1ull);
 
 struct FusedParams {
     GridDesc G;
@@ -77,23 +83,29 @@ struct FusedParams {
 template <int G> struct __align__(16) TeamShared {
     double vx[NT][4];        // (X,Y,Z,W), W > 0; Cartesian (x,y,z,-) during integration
     double pl[PC][4];        // half-space a x + b y + c z + d >= 0, seed-centred frame
-    // ---- from here to `pool_j` the area is re-used as the FC x FC twin table ----
+    // ---- from here to `pool_img` the area is re-used as the FC x FC twin table ----
     float ve[NT];            // forward error coefficient of the vertex
     float vr[NT];            // |v|^2, rounded up
     uint32_t mark[PC][2];    // directed dual edges of the conflict zone (bit matrix)
-    double cand[G][4];       // staged candidate planes of the current batch
-    uint32_t pool_key[POOL];
-    // ----
+    union {
+        struct {
+            uint32_t pool_key[POOL];   // (d2 as float, rounded down) & ~63 | pool index
+            uint32_t desc[G][5];       // scan rows: prefix end, a0, n0, a1, images
+        } scan;
+        struct {
+            double cand[G][4];         // staged planes of the current batch of candidates
+            float cand_m[G];           // max(|normal|max, |d|) of the plane, rounded up
+        } stage;
+    } u;
     uint32_t pool_j[POOL];
+    uint8_t pool_img[POOL];
+    // ----
     double cand_d2[G];
-    uint32_t desc[G][5];     // scan rows: prefix end, a0, n0, a1, images
+    uint32_t cand_j[G];
     uint32_t tri[NT];        // p0 | p1 << 8 | p2 << 16
     uint32_t gid[PC];        // grid-order index of the plane's neighbour seed
     float pnm[PC];           // max |normal component| of the plane, rounded up
-    uint32_t cand_j[G];
-    float cand_m[G];         // max(|normal|max, |d|) of the staged plane, rounded up
     uint16_t rec[NT];        // border edges of a cut: a | b << 8
-    uint8_t pool_img[POOL];
     uint8_t order[POOL];     // pool entries in ascending distance
     uint8_t gimg[PC];        // packed periodic image of the neighbour, kImgBox = box plane
     uint8_t cslot[NT];       // conflict slots of a cut, in slot order (= holes)
@@ -281,7 +293,7 @@ __device__ inline double coverage2(const GridDesc& Gd, double sx, double sy, dou
 }
 
 template <int G, bool FACES, int WPB>
-__global__ void __launch_bounds__(32 * WPB, 4) cells_fused_kernel(FusedParams P) {
+__global__ void __launch_bounds__(32 * WPB, B200VOR_FUSED_MINBLOCKS) cells_fused_kernel(FusedParams P) {
     constexpr int TPW = 32 / G;
     constexpr int R = NT / G;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -335,7 +347,7 @@ __global__ void __launch_bounds__(32 * WPB, 4) cells_fused_kernel(FusedParams P)
     }
     __syncwarp();
     uint32_t T = 8;                       // live slots [0,T)
-    unsigned long long live = 0x3Full;    // allocated plane slots
+    unsigned long long live = kLiveInit;  // allocated plane slots (ids >= PC never free)
     uint32_t status = 0, extra = 0;
     uint32_t nP = 0, nC = 0, nV = 0;
     float R2;
@@ -469,11 +481,11 @@ __global__ void __launch_bounds__(32 * WPB, 4) cells_fused_kernel(FusedParams P)
                 }
                 uint32_t total;
                 uint32_t pre = tm.exscan(n0 + n1, total);
-                sh->desc[lt][0] = pre + n0 + n1;
-                sh->desc[lt][1] = a0;
-                sh->desc[lt][2] = n0;
-                sh->desc[lt][3] = a1;
-                sh->desc[lt][4] = img;
+                sh->u.scan.desc[lt][0] = pre + n0 + n1;
+                sh->u.scan.desc[lt][1] = a0;
+                sh->u.scan.desc[lt][2] = n0;
+                sh->u.scan.desc[lt][3] = a1;
+                sh->u.scan.desc[lt][4] = img;
                 if(auto_hi && rb == 0) {
                     // first shell: radius of the ball expected to hold P.target seeds at
                     // the density of the scanned rows
@@ -486,7 +498,7 @@ __global__ void __launch_bounds__(32 * WPB, 4) cells_fused_kernel(FusedParams P)
                     }
                 }
                 __syncwarp();
-                uint32_t cur = 0, cur_end = sh->desc[0][0], cur_beg = 0;
+                uint32_t cur = 0, cur_end = sh->u.scan.desc[0][0], cur_beg = 0;
                 for(uint32_t c0 = 0; wany(rowact && c0 < total); c0 += G) {
                     uint32_t cc = c0 + lt;
                     bool in = false;
@@ -496,16 +508,16 @@ __global__ void __launch_bounds__(32 * WPB, 4) cells_fused_kernel(FusedParams P)
                         while(cc >= cur_end) {
                             cur_beg = cur_end;
                             ++cur;
-                            cur_end = sh->desc[cur][0];
+                            cur_end = sh->u.scan.desc[cur][0];
                         }
                         uint32_t off = cc - cur_beg;
-                        uint32_t dn0 = sh->desc[cur][2];
-                        uint32_t dimg = sh->desc[cur][4];
+                        uint32_t dn0 = sh->u.scan.desc[cur][2];
+                        uint32_t dimg = sh->u.scan.desc[cur][4];
                         if(off < dn0) {
-                            j = sh->desc[cur][1] + off;
+                            j = sh->u.scan.desc[cur][1] + off;
                             im = dimg & 0x3Fu;
                         } else {
-                            j = sh->desc[cur][3] + (off - dn0);
+                            j = sh->u.scan.desc[cur][3] + (off - dn0);
                             im = (dimg & 0x3Cu) | ((dimg >> 8) & 3u);
                         }
                         Seed sj = load_seed(P.sorted + j);
@@ -520,7 +532,7 @@ __global__ void __launch_bounds__(32 * WPB, 4) cells_fused_kernel(FusedParams P)
                         uint32_t ppos = count + __popc(bal & tm.lt_mask());
                         if(ppos < uint32_t(POOL)) {
                             uint32_t kb = __float_as_uint(__double2float_rd(d2));
-                            sh->pool_key[ppos] = (kb & ~63u) | ppos;
+                            sh->u.scan.pool_key[ppos] = (kb & ~63u) | ppos;
                             sh->pool_j[ppos] = j;
                             sh->pool_img[ppos] = uint8_t(im);
                         }
@@ -548,7 +560,7 @@ __global__ void __launch_bounds__(32 * WPB, 4) cells_fused_kernel(FusedParams P)
 #pragma unroll
             for(int r = 0; r < RP; ++r) {
                 uint32_t e = lt + G * r;
-                key[r] = (so && e < cnt) ? sh->pool_key[e] : 0xffffffffu;
+                key[r] = (so && e < cnt) ? sh->u.scan.pool_key[e] : 0xffffffffu;
             }
             if(wany(so && cnt > uint32_t(G))) {
                 bitonic_sort<G, RP>(lt, key);
@@ -573,8 +585,14 @@ __global__ void __launch_bounds__(32 * WPB, 4) cells_fused_kernel(FusedParams P)
         while(wany(!done && pos < cnt)) {
             const bool A = !done && pos < cnt;
             const uint32_t b0 = pos, bend = min(pos + uint32_t(G), cnt);
-            // ---- stage the planes of the next G candidates ----
-            if(A && b0 + lt < bend) {
+            // ---- stage the planes of the next G candidates (ascending distance) ----
+            const bool mine = A && b0 + lt < bend;
+            Plane pq;
+            pq.a = pq.b = pq.c = pq.d = 0.0;
+            double myd2 = 1e300;
+            float Mq = 0.f;
+            bool dup = false;
+            if(mine) {
                 uint32_t idx = sh->order[b0 + lt];
                 uint32_t j = sh->pool_j[idx];
                 uint32_t im = sh->pool_img[idx];
@@ -582,93 +600,83 @@ __global__ void __launch_bounds__(32 * WPB, 4) cells_fused_kernel(FusedParams P)
                 double qx = (sj.x + img_shift(im, P.period)) - si.x;
                 double qy = (sj.y + img_shift(im >> 2, P.period)) - si.y;
                 double qz = (sj.z + img_shift(im >> 4, P.period)) - si.z;
-                double d2 = qx * qx + qy * qy + qz * qz;
+                myd2 = qx * qx + qy * qy + qz * qz;
                 // plane (i,j) = (-2q, |q|^2 + wi - wj) (periodic_delaunay_3d.cpp:3719-3726,
                 // seed-centred frame)
-                double2* cp = reinterpret_cast<double2*>(sh->cand[lt]);
-                const double pd = d2 + (si.w - sj.w);
-                cp[0] = make_double2(-2.0 * qx, -2.0 * qy);
-                cp[1] = make_double2(-2.0 * qz, pd);
-                sh->cand_m[lt] = __double2float_ru(
-                    fmax(fmax(2.0 * fabs(qx), 2.0 * fabs(qy)), fmax(2.0 * fabs(qz), fabs(pd))));
-                sh->cand_d2[lt] = d2;
+                pq.a = -2.0 * qx; pq.b = -2.0 * qy; pq.c = -2.0 * qz;
+                pq.d = myd2 + (si.w - sj.w);
+                Mq = __double2float_ru(fmax(fmax(fabs(pq.a), fabs(pq.b)), fmax(fabs(pq.c), fabs(pq.d)))) * 1.0001f;
+                double2* cp = reinterpret_cast<double2*>(sh->u.stage.cand[lt]);
+                cp[0] = make_double2(pq.a, pq.b);
+                cp[1] = make_double2(pq.c, pq.d);
+                sh->u.stage.cand_m[lt] = Mq;
+                sh->cand_d2[lt] = myd2;
                 sh->cand_j[lt] = j;
                 sh->cand_img[lt] = uint8_t(im);
+                if(myd2 == 0.0) {
+                    // exact duplicate (delaunay_nn.cpp:122-135): the lower user index
+                    // keeps the cell; the duplicate itself is never a neighbour
+                    dup = im == kImg0 && __ldg(P.perm + j) < row;
+                }
+            }
+            // ---- pre-filter, lanes = candidate planes: a plane that cuts nothing of the
+            //      current cell can never cut the (smaller) later cell ----
+            bool cuts = false, tie = false;
+            {
+                const bool tst = mine && myd2 != 0.0 && myd2 <= bnd;
+                for(uint32_t s = 0; wany(tst && s < T); ++s) {
+                    if(tst && s < T) {
+                        const double2* p = reinterpret_cast<const double2*>(sh->vx[s]);
+                        double2 xy = p[0], zw = p[1];
+                        double dot = fma(pq.a, xy.x, fma(pq.b, xy.y, fma(pq.c, zw.x, pq.d * zw.y)));
+                        float E = Mq * sh->ve[s];
+                        // conflict only when CERTAINLY outside; a tie leaves the vertex
+                        // alone (reference fast mode, convex_cell.cpp:968) and flags the cell
+                        bool t1 = __double2float_rd(fabs(dot)) <= E;
+                        cuts |= !t1 && (dot < 0.0);
+                        tie |= t1;
+                    }
+                }
+                const uint32_t nt = __popc(tm.ballot(tst));
+                nP += nt;
+                nC += nt * T;
+            }
+            uint32_t flags = tm.ballot(cuts);
+            // candidates beyond the security radius end the walk (sorted: a suffix)
+            const uint32_t beyond = tm.ballot(mine && myd2 > bnd);
+            if(tm.any(tie)) {
+                status |= B200VOR_CELL_UNCERTAIN;
+            }
+            if(tm.any(dup)) {
+                extra |= B200VOR_CELL_DUPLICATE;
             }
             __syncwarp();
             for(;;) {
-                // ---- search: each team advances to its next plane that cuts ----
-                bool found = false;
-                uint32_t fk = 0;
-                for(;;) {
-                    bool Q = A && !done && !found && pos < bend;
-                    if(!wany(Q)) {
-                        break;
-                    }
-                    const uint32_t k = Q ? pos - b0 : 0u;
-                    if(Q) {
-                        double d2t = sh->cand_d2[k];
-                        if(d2t == 0.0) {
-                            // exact duplicate (delaunay_nn.cpp:122-135): the lower user
-                            // index keeps the cell
-                            if(sh->cand_img[k] == kImg0 && __ldg(P.perm + sh->cand_j[k]) < row) {
-                                extra |= B200VOR_CELL_DUPLICATE;
-                            }
-                            ++pos;
-                            Q = false;
-                        } else if(d2t > bnd) {
-                            certified = true;   // security radius reached
-                            done = true;
-                            Q = false;
-                        }
-                    }
-                    // ---- sign tests of the plane against the cell vertices ----
-                    const Plane pq = load_plane(sh->cand[k]);
-                    const float M = sh->cand_m[k] * 1.0001f;
-                    bool cfany = false, unc = false;
-#pragma unroll
-                    for(int r = 0; r < R; ++r) {
-                        uint32_t s = lt + G * r;
-                        if(Q && s < T) {
-                            const double2* p = reinterpret_cast<const double2*>(sh->vx[s]);
-                            double2 xy = p[0], zw = p[1];
-                            double dot = fma(pq.a, xy.x, fma(pq.b, xy.y, fma(pq.c, zw.x, pq.d * zw.y)));
-                            float E = M * sh->ve[s];
-                            // conflict only when CERTAINLY outside; a tie leaves the vertex
-                            // alone (reference fast mode, convex_cell.cpp:968) and flags
-                            // the cell
-                            bool tie = __double2float_rd(fabs(dot)) <= E;
-                            cfany |= !tie && (dot < 0.0);
-                            unc |= tie;
-                        }
-                    }
-                    const uint32_t bc = __ballot_sync(kFull, cfany), bu = __ballot_sync(kFull, unc);
-                    if(Q) {
-                        ++nP;
-                        nC += T;
-                        if((bu >> tm.tbase) & Team<G>::kGMask) {
-                            status |= B200VOR_CELL_UNCERTAIN;
-                        }
-                        if((bc >> tm.tbase) & Team<G>::kGMask) {
-                            found = true;
-                            fk = k;
-                        } else {
-                            ++pos;
-                        }
-                    }
-                }
+                // ---- next plane of the batch that may cut ----
+                bool found = A && !done && flags != 0u;
                 if(!wany(found)) {
                     break;
+                }
+                uint32_t fk = 0;
+                if(found) {
+                    fk = uint32_t(__ffs(int(flags))) - 1u;
+                    flags &= flags - 1u;
+                    if(sh->cand_d2[fk] > bnd) {
+                        certified = true;   // security radius reached
+                        done = true;
+                        found = false;
+                    }
                 }
                 // ================================================================ cut
                 // (triangulate_conflict_zone, convex_cell.cpp:761-865, without adjacency)
                 bool F = found;
-                const Plane pe = load_plane(sh->cand[fk]);
+                const Plane pe = load_plane(sh->u.stage.cand[fk]);
                 const uint32_t gj = sh->cand_j[fk], gi = sh->cand_img[fk];
                 uint32_t cm[R];
                 uint32_t cfbits = 0, nconf = 0;
                 {
-                    const float M = sh->cand_m[fk] * 1.0001f;
+                    const float M = sh->u.stage.cand_m[fk];
+                    bool unc = false;
 #pragma unroll
                     for(int r = 0; r < R; ++r) {
                         uint32_t s = lt + G * r;
@@ -678,16 +686,23 @@ __global__ void __launch_bounds__(32 * WPB, 4) cells_fused_kernel(FusedParams P)
                             double2 xy = p[0], zw = p[1];
                             double dot = fma(pe.a, xy.x, fma(pe.b, xy.y, fma(pe.c, zw.x, pe.d * zw.y)));
                             float E = M * sh->ve[s];
-                            bool tie = __double2float_rd(fabs(dot)) <= E;
-                            cf = !tie && (dot < 0.0);
+                            bool t1 = __double2float_rd(fabs(dot)) <= E;
+                            cf = !t1 && (dot < 0.0);
+                            unc |= t1;
                         }
                         cm[r] = tm.ballot(cf);
                         cfbits |= cf ? (1u << r) : 0u;
                         nconf += __popc(cm[r]);
                     }
+                    if(tm.any(unc) && F) {
+                        status |= B200VOR_CELL_UNCERTAIN;
+                    }
+                    nC += F ? T : 0u;
+                }
+                if(F && nconf == 0) {
+                    F = false;   // the cell shrank since the pre-filter: no longer cut
                 }
                 if(F) {
-                    ++pos;
                     if(nconf == T) {
                         T = 0;
                         status |= B200VOR_CELL_EMPTY;
@@ -719,7 +734,7 @@ __global__ void __launch_bounds__(32 * WPB, 4) cells_fused_kernel(FusedParams P)
                     ulo = tm.or_u32(ulo);
                     uhi = tm.or_u32(uhi);
                     if(F && live == ~0ull) {
-                        live = ((unsigned long long)ulo | ((unsigned long long)uhi << 32)) | 0x3Full;
+                        live = ((unsigned long long)ulo | ((unsigned long long)uhi << 32)) | kLiveInit;
                         if(live == ~0ull) {
                             status |= B200VOR_CELL_OVERFLOW;
                             done = true;
@@ -880,6 +895,13 @@ __global__ void __launch_bounds__(32 * WPB, 4) cells_fused_kernel(FusedParams P)
                     }
                 }
             }
+            if(A) {
+                pos = bend;
+                if(beyond != 0u && !done) {
+                    certified = true;   // every candidate up to the security radius was offered
+                    done = true;
+                }
+            }
         }
     }
     status |= extra;
@@ -939,7 +961,7 @@ __global__ void __launch_bounds__(32 * WPB, 4) cells_fused_kernel(FusedParams P)
         }
     }
     uint8_t* table = reinterpret_cast<uint8_t*>(sh->ve);
-    static_assert(offsetof(TeamShared<G>, pool_j) - offsetof(TeamShared<G>, ve) >= FC * FC,
+    static_assert(offsetof(TeamShared<G>, cand_d2) - offsetof(TeamShared<G>, ve) >= FC * FC,
                   "twin table does not fit its overlay");
     __syncwarp();
     for(uint32_t k = lt; k < uint32_t(FC * FC) / 4u; k += G) {
@@ -1125,6 +1147,9 @@ int run_cells_fused(Ctx* c, uint32_t nq, const uint32_t* qlist, int want_faces, 
     P.fcap = c->fcap;
     P.evcount = collect_events ? c->evcount.p : nullptr;
     P.target = target > 0.f ? target : 40.f;
+    if(const char* e = getenv("B200VOR_TARGET")) {   // development knob
+        P.target = float(atof(e));
+    }
     constexpr int G = 16, WPB = 4, TPW = 32 / G;
     size_t smem = sizeof(TeamShared<G>) * TPW * WPB;
     uint32_t nblk = (nq + TPW * WPB - 1) / (TPW * WPB);

@@ -139,7 +139,7 @@ int b200vor_set_query_range(b200vor_ctx* ctx, uint32_t first, uint32_t last);
 
 /* ---- introspection ---- */
 int b200vor_get_stats(b200vor_ctx* ctx, b200vor_stats* stats);
-/* tuning knob: target points per grid cell (default 4.0); takes effect at the next set_points */
+/* tuning knob: target points per grid cell (default 8.0); takes effect at the next set_points */
 int b200vor_set_points_per_cell(b200vor_ctx* ctx, double ppc);
 
 #ifdef __cplusplus
