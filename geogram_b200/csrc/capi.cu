@@ -548,6 +548,7 @@ int b200vor_compute_cells(b200vor_ctx* h, const b200vor_cell_params* params) {
     B200_CUDA_CHECK(cudaSetDevice(c->device));
     if(c->grid_dirty || c->grid.periodic != c->periodic ||
        (c->periodic && c->grid.period != c->period)) {
+        c->stats.ms_grid = 0.f;
         int rc = ensure_grid(c);   // points moved (Lloyd) or the domain changed after set_points
         if(rc) {
             return rc;
@@ -617,6 +618,9 @@ int b200vor_lloyd(b200vor_ctx* h, uint32_t iters, const b200vor_cell_params* par
     p.want_faces = 0;
     int rc;
     c->stats.ms_knn = c->stats.ms_clip = 0.f;
+    if(c->grid_dirty) {
+        c->stats.ms_grid = 0.f;   // a clean grid keeps the time of the build that made it
+    }
     for(uint32_t it = 0; it < iters; ++it) {
         if(c->grid_dirty && (rc = ensure_grid(c))) {
             return rc;

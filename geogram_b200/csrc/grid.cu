@@ -188,6 +188,40 @@ __global__ void bin_scatter_kernel(const double* __restrict__ xyz,
     perm[pos] = i;
 }
 
+// Orders the seeds of every bin by user index.  bin_count hands out ranks with atomics, so
+// the order inside a bin would otherwise change from run to run, and with it the order in
+// which equidistant neighbours are clipped (results identical to rounding, not bitwise).
+// The ranks are almost sorted already: this is one read of perm plus rare moves.
+__global__ void sort_bins_kernel(uint32_t ncell, const uint32_t* __restrict__ cell_start,
+                                 Seed* __restrict__ sorted, uint32_t* __restrict__ perm) {
+    uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if(c >= ncell) {
+        return;
+    }
+    const uint32_t a = cell_start[c], b = cell_start[c + 1];
+    for(uint32_t i = a + 1; i < b; ++i) {
+        const uint32_t key = perm[i];
+        if(perm[i - 1] <= key) {
+            continue;
+        }
+        const double2* src = reinterpret_cast<const double2*>(sorted + i);
+        const double2 s0 = src[0], s1 = src[1];
+        uint32_t j = i;
+        while(j > a && perm[j - 1] > key) {
+            perm[j] = perm[j - 1];
+            double2* dst = reinterpret_cast<double2*>(sorted + j);
+            const double2* from = reinterpret_cast<const double2*>(sorted + j - 1);
+            dst[0] = from[0];
+            dst[1] = from[1];
+            --j;
+        }
+        perm[j] = key;
+        double2* dst = reinterpret_cast<double2*>(sorted + j);
+        dst[0] = s0;
+        dst[1] = s1;
+    }
+}
+
 }  // namespace
 
 int build_grid(Ctx* c) {
@@ -283,7 +317,9 @@ int build_grid(Ctx* c) {
     bin_scatter_kernel<<<nblk, kThreads, 0, st>>>(c->xyz.p, c->has_w ? c->wgt.p : nullptr, n,
                                                   c->cellid.p, c->rank.p, c->cell_start.p,
                                                   c->sorted.p, c->perm.p);
-    c->stats.gpu_launches += 5;
+    sort_bins_kernel<<<(G.ncell + kThreads - 1) / kThreads, kThreads, 0, st>>>(
+        G.ncell, c->cell_start.p, c->sorted.p, c->perm.p);
+    c->stats.gpu_launches += 6;
     B200_CUDA_CHECK(cudaGetLastError());
     return B200VOR_OK;
 }
