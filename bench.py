@@ -183,7 +183,8 @@ def main():
     ctx.set_domain_periodic(1.0)
     if args.ppc > 0:
         ctx.set_points_per_cell(args.ppc)
-    lo, hi = rank * n_per, (rank + 1) * n_per
+    from geogram_b200.sharding import allgather_rows, shard_range
+    lo, hi = shard_range(n_total, rank, world)
     if world > 1:
         ctx.set_query_range(lo, hi)
     ctx.set_points_device(n_total, full.data_ptr())
@@ -193,7 +194,7 @@ def main():
             ctx.lloyd_device(1, None, k0=args.k0, mode=args.mode)     # seeds stay resident, updated in place
         else:
             ctx.lloyd_device(1, out.data_ptr(), k0=args.k0, mode=args.mode)
-            dist.all_gather_into_tensor(full, out[lo:hi])  # NCCL over NVLink
+            allgather_rows(dist, full, out[lo:hi])         # NCCL over NVLink
             ctx.set_points_device(n_total, full.data_ptr())
 
     def barrier():
@@ -232,6 +233,9 @@ def main():
     e2e_steps = min(args.steps, 5)
     host_in = torch.empty((n_total, 3), dtype=torch.float64).pin_memory()
     host_out = torch.empty((n_total, 3), dtype=torch.float64).pin_memory()
+    if world == 1:
+        ctx.lloyd_device(0, full.data_ptr())     # the seeds as relaxed by the timed steps
+        torch.cuda.synchronize()
     host_in.copy_(full.cpu())
     hin, hout = host_in.numpy(), host_out.numpy()
     ectx = Context(local_rank)
@@ -240,8 +244,15 @@ def main():
         ectx.set_query_range(lo, hi)
 
     def e2e_step():
+        t_a = time.perf_counter()
         ectx.set_points(hin)                                     # H2D inside
+        t_b = time.perf_counter()
         ectx.lloyd(1, k0=args.k0, mode=args.mode, out=hout)      # D2H of the result inside
+        if os.environ.get("B200VOR_BENCH_DEBUG"):
+            st = ectx.stats()
+            sys.stderr.write("e2e step: set_points %.1f ms, lloyd %.1f ms, stats grid %.1f knn %.1f clip %.1f passes %s\n" % (
+                1e3 * (t_b - t_a), 1e3 * (time.perf_counter() - t_b), st["ms_grid"], st["ms_knn"], st["ms_clip"],
+                st["n_pass"][: st["passes"]]))
 
     e2e_step()
     barrier()
@@ -263,25 +274,49 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant phase (per step), HBM peak from MEASURED_PEAKS.json ----
+    # ---- roofline of the dominant kernel (per launch), HBM peak from MEASURED_PEAKS.json ----
+    # The dominant kernel is cells_fused_kernel (one launch per step).  Its duration is
+    # measured live with CUDA events recorded by the library on the launching stream
+    # (stats ms_clip).  Algorithmic HBM bytes per cell: read Seed 32 + perm 4
+    # + cell_start 4/ppc, write m 8 + mg 24 + status 1.
     peak, peak_src = load_peaks()
-    k_eff = last["k_pass"][0] + 1
     per_step = {k: v / args.steps for k, v in phase.items()}
-    dom = max(("ms_knn", "ms_clip", "ms_grid"), key=lambda k: per_step[k])
     n_cells = n_per
-    # algorithmic HBM bytes per cell:
-    #   grid : read xyz 24, write Seed 32 + perm 4                              = 60 B/seed (all seeds)
-    #   knn  : read Seed 32, write row 4(k+1)                                   = 32+4(k+1) B/cell
-    #   clip : read row 4(k+1), Seed 32 + perm 4, write m 8 + mg 24 + status 1  = 69+4(k+1) B/cell
-    alg = {"ms_grid": 60.0 * n_total, "ms_knn": (32.0 + 4 * k_eff) * n_cells,
-           "ms_clip": (69.0 + 4 * k_eff) * n_cells}
-    achieved = alg[dom] / (per_step[dom] * 1e-3) / 1e9
-    roofline = {"kernel": {"ms_knn": "knn_kernel", "ms_clip": "cells_knn_kernel",
-                           "ms_grid": "bin_count+scan+bin_scatter"}[dom],
-                "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                "ms_per_step": per_step[dom],
-                "note": "dominant phase is latency/FP64-issue bound, not HBM bound; see DESIGN.md"}
+    ppc_used = args.ppc if args.ppc > 0 else 8.0
+    bytes_per_cell = 32.0 + 4.0 + 4.0 / ppc_used + 8.0 + 24.0 + 1.0
+    fused = last["k_pass"][0] == 0
+    if fused:
+        kernel, kms = "cells_fused_kernel", per_step["ms_clip"]
+        alg_bytes = bytes_per_cell * n_cells
+    else:
+        k_eff = last["k_pass"][0] + 1
+        dom = max(("ms_knn", "ms_clip"), key=lambda k: per_step[k])
+        kernel = {"ms_knn": "knn_kernel", "ms_clip": "cells_knn_kernel"}[dom]
+        kms = per_step[dom]
+        alg_bytes = ((32.0 + 4 * k_eff) if dom == "ms_knn" else (69.0 + 4 * k_eff)) * n_cells
+    achieved = alg_bytes / (kms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_fused_traffic.json")
+    if fused and os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        if int(tj.get("seeds", 0)) == n_cells:
+            traffic = tj["dram_bytes_per_launch"]     # ncu --set full, dram__bytes_read+write
+    # flop model of SURVEY 8(d): 12 P + 7 C + 64 V + 45 I per cell, from the event counters of
+    # one untimed compute_cells() call on the same seeds
+    ctx.compute_cells()
+    ev = ctx.stats()
+    flops = 12.0 * ev["sum_planes"] + 7.0 * ev["sum_tests"] + 64.0 * ev["sum_created"] + 45.0 * ev["sum_tets"]
+    roofline = {"kernel": kernel, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "kernel_ms_per_launch": kms, "algorithmic_bytes_per_cell": bytes_per_cell,
+                "flop_model": {"sum_planes": ev["sum_planes"], "sum_tests": ev["sum_tests"],
+                               "sum_created": ev["sum_created"], "sum_tets": ev["sum_tets"],
+                               "grid_scans_per_cell": ev["sum_scans"] / max(n_cells, 1),
+                               "flop_per_cell": flops / max(n_cells, 1),
+                               "achieved_tflops": flops / (kms * 1e-3) / 1e12,
+                               "fp64_peak_tflops_nominal": 37.0},
+                "note": "issue/latency-bound kernel (ncu: 47% issue-active, fp64 pipe 9%); neither "
+                        "DRAM nor tensor bound, see DESIGN.md 4.2 and profiles/"}
 
     cpu = None
     if world == 1 and not args.no_cpu:

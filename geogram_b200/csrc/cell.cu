@@ -686,7 +686,7 @@ __global__ void __launch_bounds__(32 * WPB) cells_knn_kernel(CellParams P) {
     if(lane == 0) {
         P.status[row] = uint8_t(C.status);
         if(P.evcount) {
-            P.evcount[2 * size_t(row)] = min(C.nP, 0xffffu) | (min(C.nV, 0xffffu) << 16);
+            P.evcount[2 * size_t(row)] = min(C.nP, 0xffffu) | (min(C.nV, 0xfffu) << 16);
             P.evcount[2 * size_t(row) + 1] = min(C.nC, 0xfffffu) | (ntri << 20);
         }
     }
@@ -787,13 +787,14 @@ __global__ void lloyd_kernel(uint32_t n, uint32_t u0, double* __restrict__ xyz,
 __global__ void reduce_events_kernel(uint32_t n, const uint32_t* __restrict__ ev,
                                      const uint8_t* __restrict__ status,
                                      unsigned long long* __restrict__ sums) {
-    // sums: 0..3 = P, C, V, I ; 4.. = status bit counts (6 bits)
-    unsigned long long acc[11] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    // sums: 0..3 = P, C, V, I ; 4..10 = status bit counts ; 11 = grid scans (fused walk)
+    unsigned long long acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         if(ev) {
             uint32_t a = ev[2 * size_t(i)], b = ev[2 * size_t(i) + 1];
             acc[0] += a & 0xffffu;
-            acc[2] += a >> 16;
+            acc[2] += (a >> 16) & 0xfffu;
+            acc[11] += a >> 28;
             acc[1] += b & 0xfffffu;
             acc[3] += 3ull * (b >> 20);
         }
@@ -802,7 +803,7 @@ __global__ void reduce_events_kernel(uint32_t n, const uint32_t* __restrict__ ev
             acc[4 + k] += (s >> k) & 1u;
         }
     }
-    for(int k = 0; k < 11; ++k) {
+    for(int k = 0; k < 12; ++k) {
         unsigned long long v = acc[k];
         for(int o = 16; o > 0; o >>= 1) {
             v += __shfl_xor_sync(kFull, v, o);
@@ -932,6 +933,7 @@ int reduce_events(Ctx* c) {
     c->stats.n_overflow = uint32_t(h[8]);
     c->stats.n_duplicate = uint32_t(h[9]);
     c->stats.n_degenerate = uint32_t(h[10]);
+    c->stats.sum_scans = h[11];
     return B200VOR_OK;
 }
 

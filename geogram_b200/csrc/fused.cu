@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(32 * WPB, B200VOR_FUSED_MINBLOCKS) cells_fused
     uint32_t T = 8;                       // live slots [0,T)
     unsigned long long live = kLiveInit;  // allocated plane slots (ids >= PC never free)
     uint32_t status = 0, extra = 0;
-    uint32_t nP = 0, nC = 0, nV = 0;
+    uint32_t nP = 0, nC = 0, nV = 0, nscan = 0;
     float R2;
     {
         uint32_t rb = lt < 8 ? __float_as_uint(sh->vr[lt]) : 0u;
@@ -436,10 +436,29 @@ __global__ void __launch_bounds__(32 * WPB, B200VOR_FUSED_MINBLOCKS) cells_fused
                 const bool rowact = sc && rb < nrows;
                 int rowi = rb + int(lt);
                 uint32_t a0 = 0, n0 = 0, a1 = 0, n1 = 0, img = 0;
+                uint32_t nbins = 0;
                 if(rowact && rowi < nrows) {
                     int dy = rowi % R1 - ring, dz = rowi / R1 - ring;
                     int y = cy + dy, z = cz + dz, sy = 0, sz = 0;
-                    bool ok = true;
+                    // the row of bins is scanned only where it meets the ball d2 < hi
+                    const double slack = 1e-9 * Gd.w[0];
+                    double dyy = dy == 0 ? 0.0
+                                         : (dy < 0 ? si.y - (Gd.lo[1] + (cy + dy + 1) * Gd.w[1])
+                                                   : (Gd.lo[1] + (cy + dy) * Gd.w[1]) - si.y);
+                    double dzz = dz == 0 ? 0.0
+                                         : (dz < 0 ? si.z - (Gd.lo[2] + (cz + dz + 1) * Gd.w[2])
+                                                   : (Gd.lo[2] + (cz + dz) * Gd.w[2]) - si.z);
+                    dyy = fmax(dyy - slack, 0.0);
+                    dzz = fmax(dzz - slack, 0.0);
+                    const double rem = hi - (dyy * dyy + dzz * dzz);
+                    bool ok = rem > 0.0;
+                    int xa = cx - ring, xb = cx + ring;
+                    if(ok) {
+                        const double rx = sqrt(rem) + slack;
+                        xa = max(xa, int(floor((si.x - rx - Gd.lo[0]) * Gd.inv_w[0])));
+                        xb = min(xb, int(floor((si.x + rx - Gd.lo[0]) * Gd.inv_w[0])));
+                        ok = xa <= xb;
+                    }
                     if(y < 0 || y >= Gd.g[1]) {
                         if(Gd.periodic) {
                             sy = y < 0 ? -1 : 1;
@@ -459,10 +478,12 @@ __global__ void __launch_bounds__(32 * WPB, B200VOR_FUSED_MINBLOCKS) cells_fused
                     if(ok) {
                         const int gx = Gd.g[0];
                         uint32_t base = uint32_t(gx) * (uint32_t(y) + uint32_t(Gd.g[1]) * uint32_t(z));
-                        int xa = cx - ring, xb = cx + ring;
                         int ma = xa < 0 ? 0 : xa, mb = xb >= gx ? gx - 1 : xb;
-                        a0 = __ldg(P.cell_start + base + ma);
-                        n0 = __ldg(P.cell_start + base + mb + 1) - a0;
+                        nbins = uint32_t(xb - xa + 1);
+                        if(ma <= mb) {
+                            a0 = __ldg(P.cell_start + base + ma);
+                            n0 = __ldg(P.cell_start + base + mb + 1) - a0;
+                        }
                         int sx1 = 0;
                         if(Gd.periodic) {
                             if(xa < 0) {
@@ -486,12 +507,16 @@ __global__ void __launch_bounds__(32 * WPB, B200VOR_FUSED_MINBLOCKS) cells_fused
                 sh->u.scan.desc[lt][2] = n0;
                 sh->u.scan.desc[lt][3] = a1;
                 sh->u.scan.desc[lt][4] = img;
-                if(auto_hi && rb == 0) {
+                if(wany(auto_hi && rb == 0)) {
                     // first shell: radius of the ball expected to hold P.target seeds at
-                    // the density of the scanned rows
-                    double cells = double(min(nrows, G)) * double(R1);
-                    double vol = cells * Gd.w[0] * Gd.w[1] * Gd.w[2];
-                    if(total > 0) {
+                    // the density of the scanned bins
+                    uint32_t bins = nbins;
+#pragma unroll
+                    for(int o = G / 2; o > 0; o >>= 1) {
+                        bins += __shfl_xor_sync(kFull, bins, o, G);
+                    }
+                    double vol = double(bins) * Gd.w[0] * Gd.w[1] * Gd.w[2];
+                    if(auto_hi && rb == 0 && total > 0) {
                         float r3 = P.target * 0.2387324146378430f * float(vol) / float(total);
                         float rr = cbrtf(r3);
                         hi = fmin(double(rr * rr), hi);
@@ -542,6 +567,7 @@ __global__ void __launch_bounds__(32 * WPB, B200VOR_FUSED_MINBLOCKS) cells_fused
                 __syncwarp();
             }
             if(sc) {
+                ++nscan;
                 first = false;
                 pos = 0;
                 if(count > uint32_t(POOL)) {
@@ -1048,7 +1074,7 @@ __global__ void __launch_bounds__(32 * WPB, B200VOR_FUSED_MINBLOCKS) cells_fused
         P.mg[3 * size_t(row) + 2] = dead ? 0.0 : sgn * gz / 24.0 + mm * si.z;
         P.status[row] = uint8_t(status);
         if(P.evcount) {
-            P.evcount[2 * size_t(row)] = min(nP, 0xffffu) | (min(nV, 0xffffu) << 16);
+            P.evcount[2 * size_t(row)] = min(nP, 0xffffu) | (min(nV, 0xfffu) << 16) | (min(nscan, 15u) << 28);
             P.evcount[2 * size_t(row) + 1] = min(nC, 0xfffffu) | (T << 20);
         }
     }

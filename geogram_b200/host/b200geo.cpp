@@ -1,0 +1,317 @@
+// b200geo.cpp -- see b200geo.h.  Every device operation is one call of the C ABI
+// (include/b200vor.h); nothing here computes geometry on the CPU.
+#include "b200geo.h"
+
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <stdexcept>
+
+#include "../../include/b200vor.h"
+
+namespace B200GEO {
+
+namespace {
+
+void check(int rc, const char* what) {
+    if(rc != B200VOR_OK) {
+        throw std::runtime_error(std::string(what) + ": " + b200vor_last_error());
+    }
+}
+
+b200vor_ctx* new_context() {
+    b200vor_ctx* ctx = nullptr;
+    check(b200vor_create(&ctx, 0), "b200vor_create");
+    return ctx;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ NearestNeighborSearch
+NearestNeighborSearch::NearestNeighborSearch(coord_index_t dimension)
+    : dimension_(dimension), nb_points_(0), stride_(0), points_(nullptr), exact_(true),
+      ctx_(new_context()), table_k_(0) {}
+
+NearestNeighborSearch::~NearestNeighborSearch() { b200vor_destroy(ctx_); }
+
+NearestNeighborSearch* NearestNeighborSearch::create(coord_index_t dimension, const std::string& name) {
+    if(dimension != 3) {
+        fprintf(stderr, "[B200NN] warning: only dimension 3 is implemented (asked %d)\n", int(dimension));
+        return nullptr;
+    }
+    if(name != "default" && name != "B200NN") {
+        // the reference falls back to its default with a logger warning (nn_search.cpp:142-149)
+        fprintf(stderr, "[B200NN] warning: could not create NN search algorithm: %s, falling back to B200NN\n",
+                name.c_str());
+    }
+    return new NearestNeighborSearch(dimension);
+}
+
+void NearestNeighborSearch::set_points(index_t nb_points, const double* points) {
+    set_points(nb_points, points, dimension_);
+}
+
+void NearestNeighborSearch::set_points(index_t nb_points, const double* points, index_t stride) {
+    std::lock_guard<std::mutex> g(lock_);
+    nb_points_ = nb_points;
+    points_ = points;
+    stride_ = stride;
+    table_k_ = 0;
+    check(b200vor_set_points(ctx_, nb_points, points, stride, nullptr, 0), "NearestNeighborSearch::set_points");
+}
+
+void NearestNeighborSearch::get_nearest_neighbors(index_t nb_neighbors, const double* query_point,
+                                                  index_t* neighbors, double* neighbors_sq_dist) const {
+    std::lock_guard<std::mutex> g(lock_);
+    check(b200vor_knn_points(ctx_, 1, query_point, nb_neighbors, neighbors, neighbors_sq_dist, 0),
+          "NearestNeighborSearch::get_nearest_neighbors");
+}
+
+void NearestNeighborSearch::get_nearest_neighbors(index_t nb_neighbors, const double* query_point,
+                                                  index_t* neighbors, double* neighbors_sq_dist,
+                                                  KeepInitialValues) const {
+    // the caller's (sorted) candidates stay in the running: k best of the union
+    std::vector<index_t> nn(nb_neighbors);
+    std::vector<double> dd(nb_neighbors);
+    get_nearest_neighbors(nb_neighbors, query_point, nn.data(), dd.data());
+    std::vector<std::pair<double, index_t> > all;
+    for(index_t i = 0; i < nb_neighbors; ++i) {
+        all.push_back(std::make_pair(dd[i], nn[i]));
+        if(neighbors[i] != index_t(-1) && std::find(nn.begin(), nn.end(), neighbors[i]) == nn.end()) {
+            all.push_back(std::make_pair(neighbors_sq_dist[i], neighbors[i]));
+        }
+    }
+    std::sort(all.begin(), all.end());
+    for(index_t i = 0; i < nb_neighbors; ++i) {
+        neighbors[i] = all[i].second;
+        neighbors_sq_dist[i] = all[i].first;
+    }
+}
+
+void NearestNeighborSearch::get_nearest_neighbors(index_t nb_neighbors, index_t query_point,
+                                                  index_t* neighbors, double* neighbors_sq_dist) const {
+    if(query_point >= nb_points_) {
+        throw std::runtime_error("NearestNeighborSearch::get_nearest_neighbors: query index out of range");
+    }
+    std::lock_guard<std::mutex> g(lock_);
+    if(table_k_ < nb_neighbors) {
+        // one launch answers this query for every stored point
+        table_nbr_.resize(size_t(nb_points_) * nb_neighbors);
+        table_d2_.resize(size_t(nb_points_) * nb_neighbors);
+        check(b200vor_knn(ctx_, nb_neighbors, table_nbr_.data(), table_d2_.data(), 0),
+              "NearestNeighborSearch::get_nearest_neighbors (by index)");
+        table_k_ = nb_neighbors;
+    }
+    const index_t* r = &table_nbr_[size_t(query_point) * table_k_];
+    const double* d = &table_d2_[size_t(query_point) * table_k_];
+    std::copy(r, r + nb_neighbors, neighbors);
+    std::copy(d, d + nb_neighbors, neighbors_sq_dist);
+}
+
+index_t NearestNeighborSearch::get_nearest_neighbor(const double* query_point) const {
+    index_t result;
+    double sq_dist;
+    get_nearest_neighbors(1, query_point, &result, &sq_dist);
+    return result;
+}
+
+void NearestNeighborSearch::get_nearest_neighbors_all(index_t nb_neighbors, index_t* neighbors,
+                                                      double* sq_dist) const {
+    std::lock_guard<std::mutex> g(lock_);
+    check(b200vor_knn(ctx_, nb_neighbors, neighbors, sq_dist, 0), "NearestNeighborSearch::get_nearest_neighbors_all");
+}
+
+void NearestNeighborSearch::get_nearest_neighbors_batch(index_t nb_queries, const double* query_points,
+                                                        index_t nb_neighbors, index_t* neighbors,
+                                                        double* sq_dist) const {
+    std::lock_guard<std::mutex> g(lock_);
+    check(b200vor_knn_points(ctx_, nb_queries, query_points, nb_neighbors, neighbors, sq_dist, 0),
+          "NearestNeighborSearch::get_nearest_neighbors_batch");
+}
+
+// ------------------------------------------------------------------ Delaunay_NearestNeighbors
+Delaunay_NearestNeighbors::Delaunay_NearestNeighbors(coord_index_t dimension)
+    : NN_(nullptr), nb_vertices_(0), vertices_(nullptr), default_nb_neighbors_(20) {
+    if(dimension != 3) {
+        // Delaunay::InvalidDimension (delaunay.cpp:92-106)
+        throw std::runtime_error("Invalid dimension: dimension = " + std::to_string(int(dimension)) +
+                                 " is not supported by the B200 Delaunay_NearestNeighbors implementation");
+    }
+    NN_ = NearestNeighborSearch::create(dimension, "B200NN");
+}
+
+Delaunay_NearestNeighbors::~Delaunay_NearestNeighbors() { delete NN_; }
+
+void Delaunay_NearestNeighbors::store_neighbors(index_t v, index_t nb, const index_t* row, const double* d2) {
+    // delaunay_nn.cpp:104-145: row holds nb+1 entries, nearest first (normally v itself)
+    std::vector<index_t>& out = neighbors_[v];
+    out.clear();
+    for(index_t k = 0; k < nb + 1; ++k) {
+        index_t j = row[k];
+        if(j == index_t(-1)) {
+            break;
+        }
+        if(d2[k] == 0.0) {
+            if(j < v) {
+                out.clear();   // v duplicates a lower index: it owns no cell and no neighbours
+                return;
+            }
+            continue;          // v itself, or a duplicate with a higher index
+        }
+        out.push_back(j);
+    }
+    if(out.size() > nb) {
+        out.resize(nb);
+    }
+}
+
+void Delaunay_NearestNeighbors::set_vertices(index_t nb_vertices, const double* vertices) {
+    nb_vertices_ = nb_vertices;
+    vertices_ = vertices;
+    NN_->set_points(nb_vertices, vertices);
+    index_t nb = std::min(default_nb_neighbors_, nb_vertices - 1);
+    std::vector<index_t> nbr(size_t(nb_vertices) * (nb + 1));
+    std::vector<double> d2(size_t(nb_vertices) * (nb + 1));
+    NN_->get_nearest_neighbors_all(nb + 1, nbr.data(), d2.data());
+    neighbors_.assign(nb_vertices, std::vector<index_t>());
+    for(index_t v = 0; v < nb_vertices; ++v) {
+        store_neighbors(v, nb, &nbr[size_t(v) * (nb + 1)], &d2[size_t(v) * (nb + 1)]);
+    }
+}
+
+index_t Delaunay_NearestNeighbors::nearest_vertex(const double* p) const {
+    return NN_->get_nearest_neighbor(p);
+}
+
+void Delaunay_NearestNeighbors::get_neighbors(index_t v, std::vector<index_t>& neighbors) const {
+    neighbors = neighbors_[v];
+}
+
+void Delaunay_NearestNeighbors::enlarge_neighborhood(index_t v, index_t nb) {
+    nb = std::min(nb, nb_vertices_ - 1);
+    std::vector<index_t> row(nb + 1);
+    std::vector<double> d2(nb + 1);
+    NN_->get_nearest_neighbors(nb + 1, vertex_ptr(v), row.data(), d2.data());
+    store_neighbors(v, nb, row.data(), d2.data());
+}
+
+// ------------------------------------------------------------------ ConvexCellBatch
+ConvexCellBatch::ConvexCellBatch() : ctx_(new_context()) {}
+
+ConvexCellBatch::~ConvexCellBatch() { b200vor_destroy(ctx_); }
+
+void ConvexCellBatch::init_with_box(double xmin, double ymin, double zmin, double xmax, double ymax,
+                                    double zmax) {
+    const double box[6] = {xmin, ymin, zmin, xmax, ymax, zmax};
+    check(b200vor_set_domain_box(ctx_, box), "ConvexCellBatch::init_with_box");
+}
+
+void ConvexCellBatch::set_periodic(double period) {
+    check(b200vor_set_domain_periodic(ctx_, period), "ConvexCellBatch::set_periodic");
+}
+
+void ConvexCellBatch::compute(index_t nb_seeds, const double* xyz, const double* weights, bool with_faces) {
+    check(b200vor_set_points(ctx_, nb_seeds, xyz, 3, weights, 0), "ConvexCellBatch::compute (set_points)");
+    b200vor_cell_params p;
+    memset(&p, 0, sizeof(p));
+    p.want_faces = with_faces ? 1 : 0;
+    check(b200vor_compute_cells(ctx_, &p), "ConvexCellBatch::compute");
+    m_.resize(nb_seeds);
+    mg_.resize(3 * size_t(nb_seeds));
+    status_.resize(nb_seeds);
+    check(b200vor_get_cells(ctx_, m_.data(), mg_.data(), status_.data(), 0), "ConvexCellBatch::compute (get_cells)");
+    if(with_faces) {
+        nfaces_.resize(nb_seeds);
+        face_nbr_.resize(size_t(nb_seeds) * 64);
+        face_area_.resize(size_t(nb_seeds) * 64);
+        check(b200vor_get_faces(ctx_, nfaces_.data(), face_nbr_.data(), face_area_.data(), 64, 0),
+              "ConvexCellBatch::compute (get_faces)");
+    } else {
+        nfaces_.clear();
+        face_nbr_.clear();
+        face_area_.clear();
+    }
+}
+
+void ConvexCellBatch::compute_mg(index_t c, double& m, vec3& mg) const {
+    m = m_[c];
+    mg.x = mg_[3 * size_t(c)];
+    mg.y = mg_[3 * size_t(c) + 1];
+    mg.z = mg_[3 * size_t(c) + 2];
+}
+
+vec3 ConvexCellBatch::barycenter(index_t c) const {
+    // ConvexCell::barycenter: mg / m (convex_cell.cpp:1255-1263)
+    vec3 r;
+    double s = 1.0 / m_[c];
+    r.x = s * mg_[3 * size_t(c)];
+    r.y = s * mg_[3 * size_t(c) + 1];
+    r.z = s * mg_[3 * size_t(c) + 2];
+    return r;
+}
+
+double ConvexCellBatch::total_volume() const {
+    double s = 0.0;
+    for(size_t i = 0; i < m_.size(); ++i) {
+        s += m_[i];
+    }
+    return s;
+}
+
+// ------------------------------------------------------------------ CentroidalVoronoiTesselation
+CentroidalVoronoiTesselation::CentroidalVoronoiTesselation(coord_index_t dimension) : ctx_(nullptr) {
+    if(dimension != 3) {
+        throw std::runtime_error("CentroidalVoronoiTesselation: only dimension 3 is implemented");
+    }
+    ctx_ = new_context();
+}
+
+CentroidalVoronoiTesselation::~CentroidalVoronoiTesselation() { b200vor_destroy(ctx_); }
+
+void CentroidalVoronoiTesselation::set_domain_box(const double* box6) {
+    check(b200vor_set_domain_box(ctx_, box6), "CentroidalVoronoiTesselation::set_domain_box");
+}
+
+void CentroidalVoronoiTesselation::set_periodic(double period) {
+    check(b200vor_set_domain_periodic(ctx_, period), "CentroidalVoronoiTesselation::set_periodic");
+}
+
+void CentroidalVoronoiTesselation::set_points(index_t nb_points, const double* points) {
+    points_.assign(points, points + 3 * size_t(nb_points));
+    point_is_locked_.clear();
+}
+
+void CentroidalVoronoiTesselation::lock_point(index_t i) {
+    if(point_is_locked_.empty()) {
+        point_is_locked_.assign(nb_points(), false);
+    }
+    point_is_locked_[i] = true;
+}
+
+void CentroidalVoronoiTesselation::Lloyd_iterations(index_t nb_iter) {
+    const index_t n = nb_points();
+    if(n == 0 || nb_iter == 0) {
+        return;
+    }
+    check(b200vor_set_points(ctx_, n, points_.data(), 3, nullptr, 0), "Lloyd_iterations (set_points)");
+    if(point_is_locked_.empty()) {
+        // all iterations stay on the device
+        check(b200vor_lloyd(ctx_, nb_iter, nullptr, points_.data(), 0), "Lloyd_iterations");
+        return;
+    }
+    std::vector<double> next(points_.size());
+    for(index_t it = 0; it < nb_iter; ++it) {
+        check(b200vor_lloyd(ctx_, 1, nullptr, next.data(), 0), "Lloyd_iterations");
+        for(index_t j = 0; j < n; ++j) {
+            if(!point_is_locked_[j]) {
+                for(int c = 0; c < 3; ++c) {
+                    points_[3 * size_t(j) + c] = next[3 * size_t(j) + c];
+                }
+            }
+        }
+        check(b200vor_set_points(ctx_, n, points_.data(), 3, nullptr, 0), "Lloyd_iterations (set_points)");
+    }
+}
+
+}  // namespace B200GEO

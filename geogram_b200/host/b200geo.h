@@ -1,0 +1,178 @@
+/*
+ * b200geo.h -- C++ host side of the B200 Voronoi engine, above the C ABI (include/b200vor.h).
+ *
+ * The classes mirror the reference's interfaces for this path -- same names, argument meaning
+ * and error behaviour -- so that code written against geogram reads the same
+ * (paths relative to /root/reference/src/lib/geogram):
+ *
+ *   B200GEO::NearestNeighborSearch       GEO::NearestNeighborSearch      points/nn_search.h:69-257
+ *   B200GEO::Delaunay_NearestNeighbors   GEO::Delaunay_NearestNeighbors  delaunay/delaunay_nn.h:55-135
+ *                                        (+ Delaunay::get_neighbors      delaunay/delaunay.h:421-440)
+ *   B200GEO::ConvexCellBatch             VBW::ConvexCell queries         voronoi/convex_cell.h:657-909
+ *   B200GEO::CentroidalVoronoiTesselation  GEO::CentroidalVoronoiTesselation::Lloyd_iterations
+ *                                                                        voronoi/CVT.cpp:133-169
+ *
+ * Differences that follow from the device: queries are answered from batched launches (the
+ * reference calls get_nearest_neighbors() one query at a time from parallel_for workers,
+ * delaunay/delaunay.cpp:269-273; here the by-index overload is served from a table computed
+ * for all points in one launch), and there is NO CPU fallback: constructing an object without
+ * a CUDA device throws std::runtime_error.
+ */
+#ifndef B200GEO_H
+#define B200GEO_H
+
+#include <stdint.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+struct b200vor_ctx;
+
+namespace B200GEO {
+
+typedef uint32_t index_t;          // GEO::index_t (non-GARGANTUA build, api/defs.h:111-125)
+typedef uint32_t global_index_t;   // VBW::global_index_t
+typedef uint8_t coord_index_t;
+
+struct vec3 {
+    double x, y, z;
+};
+
+/* ids >= BOX_ID in face lists are the six planes of the clipping box (x-,x+,y-,y+,z-,z+) */
+const global_index_t BOX_ID = 0xFFFFFFF0u;
+
+class NearestNeighborSearch {
+public:
+    /* names: "B200NN", "default".  Like the reference factory (nn_search.cpp:120-150) an unknown
+       name logs a warning to stderr and falls back to the default; dimension != 3 returns nullptr. */
+    static NearestNeighborSearch* create(coord_index_t dimension, const std::string& name = "default");
+    virtual ~NearestNeighborSearch();
+
+    /* points are BORROWED like in the reference (nn_search.cpp:88-94) and copied to the device */
+    virtual void set_points(index_t nb_points, const double* points);
+    virtual bool stride_supported() const { return true; }
+    virtual void set_points(index_t nb_points, const double* points, index_t stride);
+
+    /* ascending squared distance; exact; thread-safe (serialised on the device) */
+    virtual void get_nearest_neighbors(index_t nb_neighbors, const double* query_point,
+                                       index_t* neighbors, double* neighbors_sq_dist) const;
+    struct KeepInitialValues {};
+    virtual void get_nearest_neighbors(index_t nb_neighbors, const double* query_point,
+                                       index_t* neighbors, double* neighbors_sq_dist,
+                                       KeepInitialValues dummy) const;
+    /* by stored point index: the point itself comes first (kd_tree.cpp:156-189) */
+    virtual void get_nearest_neighbors(index_t nb_neighbors, index_t query_point,
+                                       index_t* neighbors, double* neighbors_sq_dist) const;
+    index_t get_nearest_neighbor(const double* query_point) const;
+
+    /* batched forms (one launch): rows of nb_neighbors */
+    void get_nearest_neighbors_all(index_t nb_neighbors, index_t* neighbors, double* sq_dist) const;
+    void get_nearest_neighbors_batch(index_t nb_queries, const double* query_points,
+                                     index_t nb_neighbors, index_t* neighbors, double* sq_dist) const;
+
+    coord_index_t dimension() const { return dimension_; }
+    index_t nb_points() const { return nb_points_; }
+    const double* point_ptr(index_t i) const { return points_ + size_t(i) * stride_; }
+    bool exact() const { return exact_; }
+    virtual void set_exact(bool x) { exact_ = x; }   /* always exact on the device */
+    b200vor_ctx* context() const { return ctx_; }
+
+protected:
+    explicit NearestNeighborSearch(coord_index_t dimension);
+    coord_index_t dimension_;
+    index_t nb_points_;
+    index_t stride_;
+    const double* points_;
+    bool exact_;
+    b200vor_ctx* ctx_;
+    mutable std::mutex lock_;
+    mutable index_t table_k_;
+    mutable std::vector<index_t> table_nbr_;
+    mutable std::vector<double> table_d2_;
+};
+
+class Delaunay_NearestNeighbors {
+public:
+    explicit Delaunay_NearestNeighbors(coord_index_t dimension);   /* throws InvalidDimension-like */
+    ~Delaunay_NearestNeighbors();
+    void set_vertices(index_t nb_vertices, const double* vertices);
+    index_t nb_vertices() const { return nb_vertices_; }
+    const double* vertex_ptr(index_t i) const { return vertices_ + 3 * size_t(i); }
+    index_t nearest_vertex(const double* p) const;
+    NearestNeighborSearch* nn_search() { return NN_; }
+    void set_default_nb_neighbors(index_t x) { default_nb_neighbors_ = x; }
+    index_t default_nb_neighbors() const { return default_nb_neighbors_; }
+    /* neighbours of v, nearest first, v itself excluded; a point that duplicates a lower index
+       gets no neighbours, higher-index duplicates are skipped (delaunay_nn.cpp:122-135) */
+    void get_neighbors(index_t v, std::vector<index_t>& neighbors) const;
+    /* re-queries v with nb neighbours (delaunay_nn.cpp:57-71) */
+    void enlarge_neighborhood(index_t v, index_t nb);
+
+private:
+    void store_neighbors(index_t v, index_t nb, const index_t* row, const double* d2);
+    NearestNeighborSearch* NN_;
+    index_t nb_vertices_;
+    const double* vertices_;
+    index_t default_nb_neighbors_;
+    std::vector<std::vector<index_t> > neighbors_;
+};
+
+/* All cells of a seed set at once; per-cell accessors named after VBW::ConvexCell. */
+class ConvexCellBatch {
+public:
+    ConvexCellBatch();
+    ~ConvexCellBatch();
+    /* clipping box {xmin,ymin,zmin,xmax,ymax,zmax} (ConvexCell::init_with_box) -- default unit cube */
+    void init_with_box(double xmin, double ymin, double zmin, double xmax, double ymax, double zmax);
+    /* periodic cube [0,period)^3: neighbour ids are real + N*instance (periodic.h:95-99) */
+    void set_periodic(double period);
+    /* weights may be null (Voronoi) */
+    void compute(index_t nb_seeds, const double* xyz, const double* weights, bool with_faces = true);
+
+    index_t nb_cells() const { return index_t(m_.size()); }
+    bool empty(index_t c) const { return (status_[c] & 4u) != 0; }
+    uint8_t status(index_t c) const { return status_[c]; }   /* B200VOR_CELL_* bits, 0 = exact & certified */
+    double volume(index_t c) const { return m_[c]; }
+    void compute_mg(index_t c, double& m, vec3& mg) const;
+    vec3 barycenter(index_t c) const;
+    /* contributing vertices (= faces) of the cell, ascending global index */
+    index_t nb_v(index_t c) const { return nfaces_.empty() ? 0 : nfaces_[c]; }
+    global_index_t v_global_index(index_t c, index_t lv) const { return face_nbr_[size_t(c) * 64 + lv]; }
+    double facet_area(index_t c, index_t lv) const { return face_area_[size_t(c) * 64 + lv]; }
+    double total_volume() const;
+
+private:
+    b200vor_ctx* ctx_;
+    std::vector<double> m_, mg_, face_area_;
+    std::vector<uint8_t> status_;
+    std::vector<uint32_t> nfaces_, face_nbr_;
+};
+
+class CentroidalVoronoiTesselation {
+public:
+    /* volumetric CVT of the unit cube (or a periodic cube); dimension must be 3 */
+    explicit CentroidalVoronoiTesselation(coord_index_t dimension = 3);
+    ~CentroidalVoronoiTesselation();
+    void set_domain_box(const double* box6);
+    void set_periodic(double period);
+    void set_points(index_t nb_points, const double* points);
+    void resize_points(index_t nb_points) { points_.resize(3 * size_t(nb_points)); }
+    index_t nb_points() const { return index_t(points_.size() / 3); }
+    double* embedding(index_t p) { return &points_[3 * size_t(p)]; }
+    const double* embedding(index_t p) const { return &points_[3 * size_t(p)]; }
+    void lock_point(index_t i);
+    void unlock_all_points() { point_is_locked_.clear(); }
+    bool point_is_locked(index_t i) const { return !point_is_locked_.empty() && point_is_locked_[i]; }
+    /* p_j <- mg_j / m_j where m_j > 1e-30 and j is not locked (CVT.cpp:150-163) */
+    void Lloyd_iterations(index_t nb_iter);
+
+private:
+    b200vor_ctx* ctx_;
+    std::vector<double> points_;
+    std::vector<bool> point_is_locked_;
+};
+
+}  // namespace B200GEO
+
+#endif

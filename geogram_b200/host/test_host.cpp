@@ -1,0 +1,162 @@
+// test_host.cpp -- exercises the C++ host classes the way the reference's own tests exercise
+// theirs (src/tests/test_nn_search/main.cpp:150-190: every d2 row bit-equal to another
+// implementation; periodic_delaunay_3d.cpp:4349-4359: sum of cell volumes).  Needs a GPU;
+// run by tests/test_host_cpp.py (-m gpu).  Brute force below is the test's own checker.
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <algorithm>
+#include <random>
+#include <vector>
+
+#include "b200geo.h"
+
+using namespace B200GEO;
+
+static int fails = 0;
+#define EXPECT(cond)                                                     \
+    do {                                                                 \
+        if(!(cond)) {                                                    \
+            printf("FAIL %s:%d: %s\n", __FILE__, __LINE__, #cond);       \
+            ++fails;                                                     \
+        }                                                                \
+    } while(0)
+
+int main() {
+    const index_t n = 4000, k = 12;
+    std::mt19937_64 rng(12345);
+    std::uniform_real_distribution<double> U(0.0, 1.0);
+    std::vector<double> pts(3 * n);
+    for(double& x : pts) {
+        x = U(rng);
+    }
+    // ---- NearestNeighborSearch
+    NearestNeighborSearch* nn = NearestNeighborSearch::create(3, "B200NN");
+    EXPECT(nn != nullptr);
+    EXPECT(NearestNeighborSearch::create(2) == nullptr);
+    nn->set_points(n, pts.data());
+    EXPECT(nn->nb_points() == n && nn->dimension() == 3 && nn->stride_supported());
+    std::vector<index_t> nbr(k);
+    std::vector<double> d2(k);
+    int bad = 0;
+    for(index_t q = 0; q < n; q += 37) {
+        nn->get_nearest_neighbors(k, q, nbr.data(), d2.data());
+        std::vector<std::pair<double, index_t> > all(n);
+        for(index_t j = 0; j < n; ++j) {
+            double dx = pts[3 * j] - pts[3 * q], dy = pts[3 * j + 1] - pts[3 * q + 1],
+                   dz = pts[3 * j + 2] - pts[3 * q + 2];
+            volatile double s = dx * dx;   // ((dx^2)+dy^2)+dz^2, no contraction (geometry_nd.h:65-73)
+            volatile double t = dy * dy;
+            s = s + t;
+            t = dz * dz;
+            s = s + t;
+            all[j] = std::make_pair(double(s), j);
+        }
+        std::sort(all.begin(), all.end());
+        for(index_t r = 0; r < k; ++r) {
+            bad += (all[r].first != d2[r]) || (all[r].second != nbr[r]);
+        }
+        EXPECT(nbr[0] == q && d2[0] == 0.0);
+    }
+    EXPECT(bad == 0);
+    double qp[3] = {0.5, 0.5, 0.5};
+    index_t nearest = nn->get_nearest_neighbor(qp);
+    nn->get_nearest_neighbors(k, qp, nbr.data(), d2.data());
+    EXPECT(nbr[0] == nearest);
+    EXPECT(std::is_sorted(d2.begin(), d2.end()));
+    // KeepInitialValues: a fake closer candidate stays first
+    std::vector<index_t> nb2(nbr);
+    std::vector<double> dd2(d2);
+    nb2[k - 1] = nbr[k - 1];
+    nn->get_nearest_neighbors(k, qp, nb2.data(), dd2.data(), NearestNeighborSearch::KeepInitialValues());
+    EXPECT(nb2 == nbr);
+    delete nn;
+
+    // ---- Delaunay_NearestNeighbors (duplicates rule)
+    std::vector<double> dup(pts);
+    dup.insert(dup.end(), pts.begin(), pts.begin() + 3 * 5);   // 5 exact duplicates
+    Delaunay_NearestNeighbors del(3);
+    del.set_default_nb_neighbors(20);
+    del.set_vertices(n + 5, dup.data());
+    std::vector<index_t> ne;
+    del.get_neighbors(n + 2, ne);
+    EXPECT(ne.empty());                     // duplicates a lower index: no neighbours
+    del.get_neighbors(2, ne);
+    EXPECT(ne.size() >= 19 && std::find(ne.begin(), ne.end(), n + 2) == ne.end());
+    del.get_neighbors(100, ne);
+    EXPECT(ne.size() == 20);
+    del.enlarge_neighborhood(100, 40);
+    std::vector<index_t> ne2;
+    del.get_neighbors(100, ne2);
+    EXPECT(ne2.size() == 40 && std::equal(ne.begin(), ne.end(), ne2.begin()));
+    EXPECT(del.nearest_vertex(&pts[3 * 77]) == 77);
+    bool threw = false;
+    try {
+        Delaunay_NearestNeighbors d2d(2);
+    } catch(const std::exception&) {
+        threw = true;
+    }
+    EXPECT(threw);
+
+    // ---- ConvexCellBatch
+    ConvexCellBatch cells;
+    cells.compute(n, pts.data(), nullptr, true);
+    EXPECT(fabs(cells.total_volume() - 1.0) < 1e-9);
+    index_t nfsum = 0;
+    bool sym = true;
+    for(index_t c = 0; c < n; ++c) {
+        EXPECT(cells.status(c) == 0);
+        nfsum += cells.nb_v(c);
+        for(index_t lv = 0; lv < cells.nb_v(c); ++lv) {
+            global_index_t g = cells.v_global_index(c, lv);
+            if(g >= BOX_ID) {
+                continue;
+            }
+            bool back = false;
+            for(index_t l2 = 0; l2 < cells.nb_v(g); ++l2) {
+                if(cells.v_global_index(g, l2) == c) {
+                    back = fabs(cells.facet_area(g, l2) - cells.facet_area(c, lv)) < 1e-12;
+                }
+            }
+            sym = sym && back;
+        }
+        vec3 b = cells.barycenter(c);
+        EXPECT(b.x > 0 && b.x < 1 && b.y > 0 && b.y < 1 && b.z > 0 && b.z < 1);
+    }
+    EXPECT(sym);                            // face (i,j) seen from both cells, same area
+    printf("mean faces per cell (incl. box): %.3f\n", double(nfsum) / n);
+    cells.set_periodic(1.0);
+    cells.compute(n, pts.data(), nullptr, true);
+    EXPECT(fabs(cells.total_volume() - 1.0) < 1e-9);
+    nfsum = 0;
+    for(index_t c = 0; c < n; ++c) {
+        nfsum += cells.nb_v(c);
+    }
+    printf("mean faces per cell (periodic): %.3f  (Poisson-Voronoi: 15.535)\n", double(nfsum) / n);
+    EXPECT(fabs(double(nfsum) / n - 15.535) < 0.3);
+
+    // ---- CentroidalVoronoiTesselation
+    CentroidalVoronoiTesselation cvt(3);
+    cvt.set_points(n, pts.data());
+    cvt.lock_point(0);
+    cvt.Lloyd_iterations(3);
+    EXPECT(cvt.embedding(0)[0] == pts[0] && cvt.embedding(0)[1] == pts[1]);   // locked
+    double moved = 0.0;
+    for(index_t i = 1; i < n; ++i) {
+        moved = std::max(moved, fabs(cvt.embedding(i)[0] - pts[3 * i]));
+        EXPECT(cvt.embedding(i)[0] > 0 && cvt.embedding(i)[0] < 1);
+    }
+    EXPECT(moved > 1e-4);
+    // relaxed seeds: volumes more uniform
+    ConvexCellBatch c2;
+    c2.compute(n, cvt.embedding(0), nullptr, false);
+    double v0 = 0, v1 = 0;
+    for(index_t c = 0; c < n; ++c) {
+        v0 += (cells.volume(c) - 1.0 / n) * (cells.volume(c) - 1.0 / n);
+        v1 += (c2.volume(c) - 1.0 / n) * (c2.volume(c) - 1.0 / n);
+    }
+    EXPECT(v1 < 0.6 * v0);
+    printf(fails ? "host test: %d FAILURES\n" : "host test: ok\n", fails);
+    return fails ? 1 : 0;
+}

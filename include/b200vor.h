@@ -89,6 +89,8 @@ typedef struct b200vor_stats {
     uint64_t sum_tets;               /* I: integration terms                              */
     uint64_t gpu_launches;           /* kernels launched by this context so far           */
     uint32_t grid_dim[3];
+    uint32_t reserved0;
+    uint64_t sum_scans;              /* fused walk: distance-shell scans of the grid, summed over cells */
 } b200vor_stats;
 
 /* ---- life cycle ---- */

@@ -1,0 +1,55 @@
+"""The C++ host side (geogram_b200/host: mirrors of GEO::NearestNeighborSearch,
+GEO::Delaunay_NearestNeighbors, VBW::ConvexCell queries, CVT Lloyd) above the C ABI."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "geogram_b200", "lib")
+
+
+def _build():
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "geogram_b200", "csrc")])
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "geogram_b200", "host")])
+
+
+def test_host_library_exports_the_mirrored_interfaces():
+    _build()
+    out = subprocess.check_output(["nm", "-D", "--demangle", os.path.join(LIB, "libb200geo.so")]).decode()
+    for sym in [
+        "B200GEO::NearestNeighborSearch::create(",
+        "B200GEO::NearestNeighborSearch::set_points(unsigned int, double const*)",
+        "B200GEO::NearestNeighborSearch::set_points(unsigned int, double const*, unsigned int)",
+        "B200GEO::NearestNeighborSearch::get_nearest_neighbors(unsigned int, double const*, unsigned int*, double*) const",
+        "B200GEO::NearestNeighborSearch::get_nearest_neighbors(unsigned int, unsigned int, unsigned int*, double*) const",
+        "B200GEO::Delaunay_NearestNeighbors::set_vertices(unsigned int, double const*)",
+        "B200GEO::Delaunay_NearestNeighbors::enlarge_neighborhood(unsigned int, unsigned int)",
+        "B200GEO::ConvexCellBatch::compute(",
+        "B200GEO::ConvexCellBatch::compute_mg(",
+        "B200GEO::CentroidalVoronoiTesselation::Lloyd_iterations(unsigned int)",
+    ]:
+        assert sym in out, sym
+    # the host library reaches the device only through the C ABI
+    undefined = [l.split()[-1] for l in out.splitlines() if " U b200vor_" in l]
+    assert "b200vor_create" in undefined and "b200vor_compute_cells" in undefined
+    assert "cuda" not in " ".join(undefined).lower()
+
+
+def test_host_fails_loudly_without_gpu():
+    """No CPU fallback: constructing a search object without a CUDA device throws."""
+    _build()
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    p = subprocess.run([os.path.join(LIB, "test_host")], capture_output=True, text=True)
+    assert p.returncode != 0
+    assert "no CUDA device" in (p.stderr + p.stdout) or "b200vor_create" in (p.stderr + p.stdout)
+
+
+@pytest.mark.gpu
+def test_host_cpp_on_gpu():
+    p = subprocess.run([os.path.join(LIB, "test_host")], capture_output=True, text=True, timeout=600)
+    print(p.stdout[-2000:], p.stderr[-2000:])
+    assert p.returncode == 0
+    assert "host test: ok" in p.stdout
