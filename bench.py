@@ -170,7 +170,6 @@ def main():
     gen.manual_seed(12345 + rank)
     mine = torch.rand((n_per, 3), dtype=torch.float64, device=dev, generator=gen)
     full = torch.empty((n_total, 3), dtype=torch.float64, device=dev)
-    out = torch.empty((n_total, 3), dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_gather_into_tensor(full, mine)
     else:
@@ -179,23 +178,17 @@ def main():
 
     stream = torch.cuda.current_stream()
     ctx = Context(local_rank)
-    ctx.set_stream(stream.cuda_stream)
     ctx.set_domain_periodic(1.0)
     if args.ppc > 0:
         ctx.set_points_per_cell(args.ppc)
-    from geogram_b200.sharding import allgather_rows, shard_range
-    lo, hi = shard_range(n_total, rank, world)
-    if world > 1:
-        ctx.set_query_range(lo, hi)
-    ctx.set_points_device(n_total, full.data_ptr())
+    from geogram_b200.sharding import ShardedLloyd
+    job = ShardedLloyd(ctx, n_total, dist if world > 1 else None, dev, stream)
+    lo, hi = job.first, job.last
+    job.set_seeds_device(full)
+    del full
 
     def step():
-        if world == 1:
-            ctx.lloyd_device(1, None, k0=args.k0, mode=args.mode)     # seeds stay resident, updated in place
-        else:
-            ctx.lloyd_device(1, out.data_ptr(), k0=args.k0, mode=args.mode)
-            allgather_rows(dist, full, out[lo:hi])         # NCCL over NVLink
-            ctx.set_points_device(n_total, full.data_ptr())
+        job.step(k0=args.k0, mode=args.mode)
 
     def barrier():
         if world > 1:
@@ -205,7 +198,8 @@ def main():
     for _ in range(args.warmup):
         step()
     launches0 = ctx.stats()["gpu_launches"]
-    phase = {"ms_grid": 0.0, "ms_knn": 0.0, "ms_clip": 0.0}
+    job.phase = {k: 0.0 for k in job.phase}
+    job.comm_ms()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
@@ -214,45 +208,32 @@ def main():
     e0.record(stream)
     for _ in range(args.steps):
         step()
-        s = ctx.stats()
-        for k in phase:
-            phase[k] += s[k]
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
     clocks = sampler.summary() if sampler else None
     launches = ctx.stats()["gpu_launches"] - launches0
     last = ctx.stats()
+    phase = dict(job.phase)
+    phase["ms_allgather"] = job.comm_ms()
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     value = n_total * args.steps / (ms * 1e-3)
 
-    # ---- end to end through the C ABI with HOST buffers (pinned), H2D + D2H inside ----
+    # ---- end to end through the public API with HOST buffers (pinned): every step uploads this
+    #      rank's rows (H2D), exchanges them over NVLink (N>1), runs the Lloyd iteration and reads
+    #      this rank's updated rows back (D2H) ----
     e2e_steps = min(args.steps, 5)
-    host_in = torch.empty((n_total, 3), dtype=torch.float64).pin_memory()
-    host_out = torch.empty((n_total, 3), dtype=torch.float64).pin_memory()
-    if world == 1:
-        ctx.lloyd_device(0, full.data_ptr())     # the seeds as relaxed by the timed steps
-        torch.cuda.synchronize()
-    host_in.copy_(full.cpu())
-    hin, hout = host_in.numpy(), host_out.numpy()
-    ectx = Context(local_rank)
-    ectx.set_domain_periodic(1.0)
-    if world > 1:
-        ectx.set_query_range(lo, hi)
+    host_in = torch.empty((hi - lo, 3), dtype=torch.float64).pin_memory()
+    host_out = torch.empty((hi - lo, 3), dtype=torch.float64).pin_memory()
+    job.get_shard_host(host_in)        # the seeds as relaxed by the timed steps
 
     def e2e_step():
-        t_a = time.perf_counter()
-        ectx.set_points(hin)                                     # H2D inside
-        t_b = time.perf_counter()
-        ectx.lloyd(1, k0=args.k0, mode=args.mode, out=hout)      # D2H of the result inside
-        if os.environ.get("B200VOR_BENCH_DEBUG"):
-            st = ectx.stats()
-            sys.stderr.write("e2e step: set_points %.1f ms, lloyd %.1f ms, stats grid %.1f knn %.1f clip %.1f passes %s\n" % (
-                1e3 * (t_b - t_a), 1e3 * (time.perf_counter() - t_b), st["ms_grid"], st["ms_knn"], st["ms_clip"],
-                st["n_pass"][: st["passes"]]))
+        job.set_shard_host(host_in)
+        job.step(k0=args.k0, mode=args.mode)
+        job.get_shard_host(host_out)
 
     e2e_step()
     barrier()
@@ -266,7 +247,6 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e_value = n_total * e2e_steps / e2e_s
-    ectx.close()
     del host_in, host_out
 
     if rank != 0:
@@ -342,7 +322,8 @@ def main():
         "phase_ms_per_step": per_step,
         "roofline": roofline, "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "steps": e2e_steps,
-                "h2d_bytes_per_step": 24 * n_total * world, "d2h_bytes_per_step": 24 * n_total * world},
+                "h2d_bytes_per_step": 24 * n_total, "d2h_bytes_per_step": 24 * n_total,
+                "note": "whole job: every rank moves its own rows (24 B/seed each way)"},
         "gpu_launches": int(launches), "clocks": clocks,
     }
     print(json.dumps(line))

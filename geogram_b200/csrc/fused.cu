@@ -46,6 +46,12 @@ namespace {
 #ifndef B200VOR_FUSED_MINBLOCKS
 #define B200VOR_FUSED_MINBLOCKS 4
 #endif
+#ifndef B200VOR_FUSED_G
+#define B200VOR_FUSED_G 16     // lanes per cell
+#endif
+#ifndef B200VOR_FUSED_WPB
+#define B200VOR_FUSED_WPB 4    // warps per block
+#endif
 constexpr int NT = 48;      // cell-vertex (dual triangle) slots
 constexpr int PC = 40;      // plane slots (0..5 = clipping box)
 constexpr int POOL = 64;    // candidate pool
@@ -96,6 +102,7 @@ template <int G> struct __align__(16) TeamShared {
             double cand[G][4];         // staged planes of the current batch of candidates
             float cand_m[G];           // max(|normal|max, |d|) of the plane, rounded up
         } stage;
+        uint32_t pad_[144];            // keeps the overlay below >= FC*FC bytes for G < 16
     } u;
     uint32_t pool_j[POOL];
     uint8_t pool_img[POOL];
@@ -1176,7 +1183,7 @@ int run_cells_fused(Ctx* c, uint32_t nq, const uint32_t* qlist, int want_faces, 
     if(const char* e = getenv("B200VOR_TARGET")) {   // development knob
         P.target = float(atof(e));
     }
-    constexpr int G = 16, WPB = 4, TPW = 32 / G;
+    constexpr int G = B200VOR_FUSED_G, WPB = B200VOR_FUSED_WPB, TPW = 32 / G;
     size_t smem = sizeof(TeamShared<G>) * TPW * WPB;
     uint32_t nblk = (nq + TPW * WPB - 1) / (TPW * WPB);
     if(want_faces) {

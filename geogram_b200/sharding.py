@@ -41,3 +41,104 @@ def allgather_rows(dist, full, mine):
         full[at:at + sz] = scratch[r * smax: r * smax + sz]
         at += sz
     return full
+
+
+class ShardedLloyd(object):
+    """CVT Lloyd relaxation of one seed set over the GPUs of one node (one process per GPU).
+
+    Rank r owns the rows [first, last) of the seed array (`shard_range`).  Every iteration:
+    each rank computes the cells of its rows against ALL seeds (b200vor_set_query_range +
+    b200vor_lloyd), then the updated rows are all-gathered (NCCL over NVLink) and the grid is
+    rebuilt on every rank.  This is the multi-GPU form of
+    CentroidalVoronoiTesselation::Lloyd_iterations (voronoi/CVT.cpp:133-169); the reference has no
+    distributed counterpart (single address space).
+
+    `dist` is torch.distributed (already initialised) or None for a single process."""
+
+    def __init__(self, ctx, n_total, dist=None, device=None, stream=None):
+        import torch
+        self.torch = torch
+        self.ctx = ctx
+        self.dist = dist
+        self.world = dist.get_world_size() if dist is not None else 1
+        self.rank = dist.get_rank() if dist is not None else 0
+        self.n_total = int(n_total)
+        self.first, self.last = shard_range(self.n_total, self.rank, self.world)
+        self.device = device
+        self.full = torch.empty((self.n_total, 3), dtype=torch.float64, device=device)
+        # staging of the updated seeds (only the own rows are used) when sharded
+        self.out = torch.empty((self.n_total, 3), dtype=torch.float64, device=device) if self.world > 1 else None
+        # gloo / CPU tensors (host-logic tests with a stand-in context): no stream, no events
+        self.on_gpu = self.full.is_cuda
+        self.stream = None
+        if self.on_gpu:
+            self.stream = stream if stream is not None else torch.cuda.current_stream(device)
+            ctx.set_stream(self.stream.cuda_stream)
+        if self.world > 1:
+            ctx.set_query_range(self.first, self.last)
+        self.phase = {"ms_grid": 0.0, "ms_knn": 0.0, "ms_clip": 0.0}
+        self._comm = []
+
+    # ---- seeds in ----
+    def set_seeds_device(self, full):
+        """full: (n_total,3) float64 device tensor holding ALL seeds (identical on every rank)."""
+        self.full.copy_(full)
+        self.ctx.set_points_device(self.n_total, self.full.data_ptr())
+        self._take("ms_grid")
+
+    def set_shard_host(self, host_rows):
+        """host_rows: this rank's rows as a (last-first,3) float64 host tensor (pinned for speed).
+        H2D of the own rows only; the other ranks' rows arrive over NVLink."""
+        mine = self.full[self.first:self.last]
+        mine.copy_(host_rows, non_blocking=True)
+        if self.world > 1:
+            self._gather(mine)
+        self.ctx.set_points_device(self.n_total, self.full.data_ptr())
+        self._take("ms_grid")
+
+    # ---- one Lloyd iteration ----
+    def step(self, k0=0, mode=0):
+        if self.world == 1:
+            self.ctx.lloyd_device(1, None, k0=k0, mode=mode)    # seeds stay resident, updated in place
+            self._take("ms_grid", "ms_knn", "ms_clip")
+            return
+        self.ctx.lloyd_device(1, self.out.data_ptr(), k0=k0, mode=mode)
+        self._take("ms_knn", "ms_clip")
+        self._gather(self.out[self.first:self.last])
+        self.ctx.set_points_device(self.n_total, self.full.data_ptr())   # grid rebuild on the new seeds
+        self._take("ms_grid")
+
+    def get_shard_host(self, host_rows):
+        """Own rows of the current seeds -> host tensor (D2H of the own rows only)."""
+        if self.world == 1:
+            self.ctx.lloyd_device(0, self.full.data_ptr())
+        host_rows.copy_(self.full[self.first:self.last], non_blocking=True)
+        if self.on_gpu:
+            self.stream.synchronize()
+        return host_rows
+
+    def comm_ms(self):
+        """Device time of the all-gathers since the last call (CUDA events on the stream)."""
+        if not self.on_gpu:
+            return 0.0
+        self.torch.cuda.synchronize(self.device)
+        ms = sum(a.elapsed_time(b) for a, b in self._comm)
+        self._comm = []
+        return ms
+
+    # ---- internals ----
+    def _gather(self, mine):
+        if not self.on_gpu:
+            allgather_rows(self.dist, self.full, mine)
+            return
+        a = self.torch.cuda.Event(enable_timing=True)
+        b = self.torch.cuda.Event(enable_timing=True)
+        a.record(self.stream)
+        allgather_rows(self.dist, self.full, mine)
+        b.record(self.stream)
+        self._comm.append((a, b))
+
+    def _take(self, *keys):
+        s = self.ctx.stats()
+        for k in keys:
+            self.phase[k] += s[k]

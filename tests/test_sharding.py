@@ -68,3 +68,87 @@ def test_allgather_rows_gloo(world, n_total):
         assert p.exitcode == 0
     assert ok == 1.0
     assert ms == float(world)
+
+
+class _StandInContext(object):
+    """Host stand-in for geogram_b200.Context (same methods ShardedLloyd calls, raw addresses):
+    the 'Lloyd update' of a row is x <- 0.5 x + 0.25 * mean(all seeds), so a rank that missed
+    another rank's rows in the exchange gets a different answer."""
+
+    def __init__(self):
+        self.first, self.last = 0, None
+        self.calls = []
+
+    @staticmethod
+    def _view(ptr, n):
+        import ctypes
+        import numpy as np
+        return np.ctypeslib.as_array((ctypes.c_double * (3 * n)).from_address(ptr)).reshape(n, 3)
+
+    def set_stream(self, s):
+        raise AssertionError("no stream on the CPU path")
+
+    def set_query_range(self, first, last):
+        self.first, self.last = first, last
+
+    def set_points_device(self, n, ptr):
+        self.n = n
+        self.xyz = self._view(ptr, n).copy()
+        self.calls.append("set_points")
+
+    def lloyd_device(self, iters, out_ptr=None, k0=0, mode=0):
+        last = self.n if self.last is None else self.last
+        for _ in range(iters):
+            self.xyz[self.first:last] = 0.5 * self.xyz[self.first:last] + 0.25 * self.xyz.mean(axis=0)
+        if out_ptr:
+            self._view(out_ptr, self.n)[:] = self.xyz
+        self.calls.append("lloyd")
+
+    def stats(self):
+        return {"ms_grid": 1.0, "ms_knn": 0.0, "ms_clip": 2.0}
+
+
+def _lloyd_worker(rank, world, port, n_total, q):
+    from geogram_b200.sharding import ShardedLloyd
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(11)
+    seeds = torch.rand((n_total, 3), dtype=torch.float64, generator=g)
+    # single-process answer
+    ref = seeds.clone()
+    for _ in range(3):
+        ref = 0.5 * ref + 0.25 * ref.mean(dim=0)
+    job = ShardedLloyd(_StandInContext(), n_total, dist, torch.device("cpu"))
+    first, last = job.first, job.last
+    job.set_shard_host(seeds[first:last].clone())      # own rows in, the rest over the wire
+    for _ in range(3):
+        job.step()
+    mine = torch.empty((last - first, 3), dtype=torch.float64)
+    job.get_shard_host(mine)
+    err = float((mine - ref[first:last]).abs().max())
+    full_err = float((job.full - ref).abs().max())
+    t = torch.tensor([max(err, full_err)], dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        q.put((float(t.item()), job.phase, job.ctx.calls))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n_total", [(2, 600), (3, 1001)])
+def test_sharded_lloyd_gloo(world, n_total):
+    """ShardedLloyd (the multi-GPU Lloyd driver of bench.py) on world_size 2 and 3 with gloo:
+    shard upload, exchange, per-rank update of the own rows, re-gather, read-back."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_lloyd_worker, args=(r, world, port, n_total, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    err, phase, calls = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert err < 1e-14
+    assert calls == ["set_points"] + ["lloyd", "set_points"] * 3
+    assert phase["ms_clip"] == 6.0 and phase["ms_grid"] == 4.0
