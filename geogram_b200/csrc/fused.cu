@@ -101,6 +101,7 @@ template <int G> struct __align__(16) TeamShared {
         struct {
             double cand[G][4];         // staged planes of the current batch of candidates
             float cand_m[G];           // max(|normal|max, |d|) of the plane, rounded up
+            float cand_n[G];           // max |normal component| of the plane, rounded up
         } stage;
         uint32_t pad_[144];            // keeps the overlay below >= FC*FC bytes for G < 16
     } u;
@@ -110,6 +111,7 @@ template <int G> struct __align__(16) TeamShared {
     double cand_d2[G];
     uint32_t cand_j[G];
     uint32_t tri[NT];        // p0 | p1 << 8 | p2 << 16
+    uint32_t ctri[G];        // `tri` of the conflict vertices of a cut, compacted onto lanes
     uint32_t gid[PC];        // grid-order index of the plane's neighbour seed
     float pnm[PC];           // max |normal component| of the plane, rounded up
     uint16_t rec[NT];        // border edges of a cut: a | b << 8
@@ -643,6 +645,8 @@ __global__ void __launch_bounds__(32 * WPB, B200VOR_FUSED_MINBLOCKS) cells_fused
                 cp[0] = make_double2(pq.a, pq.b);
                 cp[1] = make_double2(pq.c, pq.d);
                 sh->u.stage.cand_m[lt] = Mq;
+                sh->u.stage.cand_n[lt] =
+                    __double2float_ru(fmax(fabs(pq.a), fmax(fabs(pq.b), fabs(pq.c))));
                 sh->cand_d2[lt] = myd2;
                 sh->cand_j[lt] = j;
                 sh->cand_img[lt] = uint8_t(im);
@@ -657,7 +661,9 @@ __global__ void __launch_bounds__(32 * WPB, B200VOR_FUSED_MINBLOCKS) cells_fused
             bool cuts = false, tie = false;
             {
                 const bool tst = mine && myd2 != 0.0 && myd2 <= bnd;
-                for(uint32_t s = 0; wany(tst && s < T); ++s) {
+                const uint32_t Tp = __reduce_max_sync(kFull, tst ? T : 0u);
+#pragma unroll 2
+                for(uint32_t s = 0; s < Tp; ++s) {
                     if(tst && s < T) {
                         const double2* p = reinterpret_cast<const double2*>(sh->vx[s]);
                         double2 xy = p[0], zw = p[1];
@@ -686,48 +692,64 @@ __global__ void __launch_bounds__(32 * WPB, B200VOR_FUSED_MINBLOCKS) cells_fused
             __syncwarp();
             for(;;) {
                 // ---- next plane of the batch that may cut ----
-                bool found = A && !done && flags != 0u;
-                if(!wany(found)) {
+                bool F = A && !done && flags != 0u;
+                if(!wany(F)) {
                     break;
                 }
                 uint32_t fk = 0;
-                if(found) {
+                if(F) {
                     fk = uint32_t(__ffs(int(flags))) - 1u;
                     flags &= flags - 1u;
-                    if(sh->cand_d2[fk] > bnd) {
-                        certified = true;   // security radius reached
-                        done = true;
-                        found = false;
-                    }
                 }
                 // ================================================================ cut
                 // (triangulate_conflict_zone, convex_cell.cpp:761-865, without adjacency)
-                bool F = found;
                 const Plane pe = load_plane(sh->u.stage.cand[fk]);
-                const uint32_t gj = sh->cand_j[fk], gi = sh->cand_img[fk];
-                uint32_t cm[R];
+                // ---- sign tests, lanes = vertices; the same pass refreshes the squared
+                //      radius of the current cell (convex_cell.cpp:1312-1330) ----
+                const uint32_t Tw = __reduce_max_sync(kFull, F ? T : 0u);
+                uint32_t cm[R], tr[R];
                 uint32_t cfbits = 0, nconf = 0;
                 {
                     const float M = sh->u.stage.cand_m[fk];
                     bool unc = false;
+                    uint32_t rb = 0;
 #pragma unroll
                     for(int r = 0; r < R; ++r) {
-                        uint32_t s = lt + G * r;
-                        bool cf = false;
-                        if(F && s < T) {
-                            const double2* p = reinterpret_cast<const double2*>(sh->vx[s]);
-                            double2 xy = p[0], zw = p[1];
-                            double dot = fma(pe.a, xy.x, fma(pe.b, xy.y, fma(pe.c, zw.x, pe.d * zw.y)));
-                            float E = M * sh->ve[s];
-                            bool t1 = __double2float_rd(fabs(dot)) <= E;
-                            cf = !t1 && (dot < 0.0);
-                            unc |= t1;
+                        cm[r] = 0;
+                        tr[r] = 0;
+                        if(uint32_t(G * r) < Tw) {   // warp-uniform: rounds past the last vertex are skipped
+                            uint32_t s = lt + G * r;
+                            bool cf = false;
+                            if(F && s < T) {
+                                const double2* p = reinterpret_cast<const double2*>(sh->vx[s]);
+                                double2 xy = p[0], zw = p[1];
+                                double dot = fma(pe.a, xy.x, fma(pe.b, xy.y, fma(pe.c, zw.x, pe.d * zw.y)));
+                                float E = M * sh->ve[s];
+                                bool t1 = __double2float_rd(fabs(dot)) <= E;
+                                cf = !t1 && (dot < 0.0);
+                                unc |= t1;
+                                rb = max(rb, __float_as_uint(sh->vr[s]));
+                                if(cf) {
+                                    tr[r] = sh->tri[s];
+                                }
+                            }
+                            cm[r] = tm.ballot(cf);
+                            cfbits |= cf ? (1u << r) : 0u;
+                            nconf += __popc(cm[r]);
                         }
-                        cm[r] = tm.ballot(cf);
-                        cfbits |= cf ? (1u << r) : 0u;
-                        nconf += __popc(cm[r]);
                     }
-                    if(tm.any(unc) && F) {
+                    rb = tm.max_u32(rb);
+                    const bool anyunc = tm.any(unc);
+                    if(F) {
+                        R2 = __uint_as_float(rb);
+                        bnd = sr_bound(R2);
+                        if(sh->cand_d2[fk] > bnd) {
+                            certified = true;   // security radius reached
+                            done = true;
+                            F = false;
+                        }
+                    }
+                    if(anyunc && F) {
                         status |= B200VOR_CELL_UNCERTAIN;
                     }
                     nC += F ? T : 0u;
@@ -735,15 +757,19 @@ __global__ void __launch_bounds__(32 * WPB, B200VOR_FUSED_MINBLOCKS) cells_fused
                 if(F && nconf == 0) {
                     F = false;   // the cell shrank since the pre-filter: no longer cut
                 }
-                if(F) {
-                    if(nconf == T) {
-                        T = 0;
-                        status |= B200VOR_CELL_EMPTY;
-                        R2 = 0.f;
-                        certified = true;
-                        done = true;
-                        F = false;
-                    }
+                if(F && nconf == T) {
+                    T = 0;
+                    status |= B200VOR_CELL_EMPTY;
+                    R2 = 0.f;
+                    certified = true;
+                    done = true;
+                    F = false;
+                }
+                if(F && nconf > uint32_t(G)) {
+                    // more conflict vertices than lanes: left to the kNN-table pipeline
+                    status |= B200VOR_CELL_OVERFLOW;
+                    done = true;
+                    F = false;
                 }
                 if(wany(F && live == ~0ull)) {
                     // plane table full: drop the planes no vertex refers to any more
@@ -776,79 +802,81 @@ __global__ void __launch_bounds__(32 * WPB, B200VOR_FUSED_MINBLOCKS) cells_fused
                     }
                 }
                 const uint32_t pn = uint32_t(__ffsll((long long)~live)) - 1u;
-                // ---- conflict slots in slot order (= the holes the new vertices fill) ----
+                // ---- conflict vertices compacted onto lanes, in slot order (= the holes the
+                //      new vertices fill) ----
                 {
                     uint32_t hbase = 0;
 #pragma unroll
                     for(int r = 0; r < R; ++r) {
                         if(F && ((cfbits >> r) & 1u)) {
-                            sh->cslot[hbase + __popc(cm[r] & tm.lt_mask())] = uint8_t(lt + G * r);
+                            uint32_t rk = hbase + __popc(cm[r] & tm.lt_mask());
+                            sh->cslot[rk] = uint8_t(lt + G * r);
+                            sh->ctri[rk] = tr[r];
                         }
                         hbase += __popc(cm[r]);
                     }
                 }
                 __syncwarp();
                 // ---- mark the directed edges of the conflict triangles ----
-                for(uint32_t h0 = 0; wany(F && h0 < nconf); h0 += G) {
-                    if(F && h0 + lt < nconf) {
-                        uint32_t t = sh->tri[sh->cslot[h0 + lt]];
-                        uint32_t p0 = t & 0xffu, p1 = (t >> 8) & 0xffu, p2 = (t >> 16) & 0xffu;
-                        atomicOr(&sh->mark[p0][p1 >> 5], 1u << (p1 & 31u));
-                        atomicOr(&sh->mark[p1][p2 >> 5], 1u << (p2 & 31u));
-                        atomicOr(&sh->mark[p2][p0 >> 5], 1u << (p0 & 31u));
-                    }
+                const bool Q = F && lt < nconf;
+                uint32_t p0 = 0, p1 = 0, p2 = 0;
+                if(Q) {
+                    uint32_t t = sh->ctri[lt];
+                    p0 = t & 0xffu; p1 = (t >> 8) & 0xffu; p2 = (t >> 16) & 0xffu;
+                    atomicOr(&sh->mark[p0][p1 >> 5], 1u << (p1 & 31u));
+                    atomicOr(&sh->mark[p1][p2 >> 5], 1u << (p2 & 31u));
+                    atomicOr(&sh->mark[p2][p0 >> 5], 1u << (p0 & 31u));
                 }
                 __syncwarp();
                 // ---- border edges (twin not marked) -> records ----
-                uint32_t nnew = 0;
-                for(uint32_t h0 = 0; wany(F && h0 < nconf); h0 += G) {
-                    uint32_t bits = 0, t = 0;
-                    if(F && h0 + lt < nconf) {
-                        t = sh->tri[sh->cslot[h0 + lt]];
-#pragma unroll
-                        for(int e = 0; e < 3; ++e) {
-                            uint32_t u = (t >> (8 * e)) & 0xffu, v = (t >> (8 * ((e + 1) % 3))) & 0xffu;
-                            uint32_t twin = (sh->mark[v][u >> 5] >> (u & 31u)) & 1u;
-                            bits |= (twin ^ 1u) << e;
+                uint32_t bits = 0;
+                if(Q) {
+                    bits = (((sh->mark[p1][p0 >> 5] >> (p0 & 31u)) & 1u) ^ 1u) |
+                           ((((sh->mark[p2][p1 >> 5] >> (p1 & 31u)) & 1u) ^ 1u) << 1) |
+                           ((((sh->mark[p0][p2 >> 5] >> (p2 & 31u)) & 1u) ^ 1u) << 2);
+                }
+                uint32_t nnew;
+                {
+                    uint32_t rk = tm.exscan(__popc(bits), nnew);
+                    if(F && nnew > uint32_t(G)) {
+                        // a new face with more vertices than lanes: kNN-table pipeline
+                        status |= B200VOR_CELL_OVERFLOW;
+                        done = true;
+                        F = false;
+                    }
+                    if(F) {
+                        if(bits & 1u) {
+                            sh->rec[rk++] = uint16_t(p0 | (p1 << 8));
+                        }
+                        if(bits & 2u) {
+                            sh->rec[rk++] = uint16_t(p1 | (p2 << 8));
+                        }
+                        if(bits & 4u) {
+                            sh->rec[rk] = uint16_t(p2 | (p0 << 8));
                         }
                     }
-                    uint32_t tot;
-                    uint32_t rk = nnew + tm.exscan(__popc(bits), tot);
-#pragma unroll
-                    for(int e = 0; e < 3; ++e) {
-                        if(((bits >> e) & 1u) && rk < uint32_t(NT)) {
-                            uint32_t u = (t >> (8 * e)) & 0xffu, v = (t >> (8 * ((e + 1) % 3))) & 0xffu;
-                            sh->rec[rk++] = uint16_t(u | (v << 8));
-                        }
-                    }
-                    nnew += tot;
                 }
                 __syncwarp();
-                for(uint32_t h0 = 0; wany(F && h0 < nconf); h0 += G) {
-                    if(F && h0 + lt < nconf) {
-                        uint32_t t = sh->tri[sh->cslot[h0 + lt]];
-                        uint32_t p0 = t & 0xffu, p1 = (t >> 8) & 0xffu, p2 = (t >> 16) & 0xffu;
-                        *reinterpret_cast<uint2*>(sh->mark[p0]) = make_uint2(0u, 0u);
-                        *reinterpret_cast<uint2*>(sh->mark[p1]) = make_uint2(0u, 0u);
-                        *reinterpret_cast<uint2*>(sh->mark[p2]) = make_uint2(0u, 0u);
-                    }
+                // the whole bit matrix is cleared with two vector stores per lane
+                for(uint32_t k = lt; k < uint32_t(PC * 8 / 16); k += G) {
+                    reinterpret_cast<uint4*>(&sh->mark[0][0])[k] = make_uint4(0u, 0u, 0u, 0u);
                 }
                 uint32_t Tnew = T - nconf + nnew;
-                if(F && (Tnew > uint32_t(NT) || nnew > uint32_t(NT))) {
+                if(F && Tnew > uint32_t(NT)) {
                     status |= B200VOR_CELL_OVERFLOW;
                     done = true;
                     F = false;
                 }
+                const float npn = sh->u.stage.cand_n[fk];
                 if(F) {
                     live |= 1ull << pn;
                     if(lt == 0) {
-                        const float npn_pl = __double2float_ru(fmax(fabs(pe.a), fmax(fabs(pe.b), fabs(pe.c))));
                         double2* p = reinterpret_cast<double2*>(sh->pl[pn]);
                         p[0] = make_double2(pe.a, pe.b);
                         p[1] = make_double2(pe.c, pe.d);
-                        sh->gid[pn] = gj;
-                        sh->gimg[pn] = uint8_t(gi);
-                        sh->pnm[pn] = npn_pl;
+                        sh->gid[pn] = sh->cand_j[fk];
+                        sh->gimg[pn] = sh->cand_img[fk];
+                        sh->pnm[pn] = npn;
                     }
                 }
                 // ---- fewer new vertices than holes (two faces vanished at once): the
@@ -892,40 +920,38 @@ __global__ void __launch_bounds__(32 * WPB, B200VOR_FUSED_MINBLOCKS) cells_fused
                         }
                     }
                 }
-                // ---- one new vertex per border edge ----
-                const float npn = __double2float_ru(fmax(fabs(pe.a), fmax(fabs(pe.b), fabs(pe.c))));
-                for(uint32_t k0 = 0; wany(F && k0 < nnew); k0 += G) {
-                    uint32_t kk = k0 + lt;
-                    if(F && kk < nnew) {
-                        uint32_t rr = sh->rec[kk];
-                        uint32_t u = rr & 0xffu, v = rr >> 8;
-                        uint32_t s = kk < nconf ? uint32_t(sh->cslot[kk]) : T + (kk - nconf);
-                        Vertex V = make_vertex(pe, load_plane(sh->pl[u]), load_plane(sh->pl[v]), npn,
-                                               sh->pnm[u], sh->pnm[v]);
-                        degenerate |= V.degenerate;
-                        store_vertex<G>(sh, s, V, pn | (u << 8) | (v << 16));
-                    }
+                // ---- one new vertex per border edge, one lane each ----
+                if(F && lt < nnew) {
+                    uint32_t rr = sh->rec[lt];
+                    uint32_t u = rr & 0xffu, v = rr >> 8;
+                    uint32_t s = lt < nconf ? uint32_t(sh->cslot[lt]) : T + (lt - nconf);
+                    Vertex V = make_vertex(pe, load_plane(sh->pl[u]), load_plane(sh->pl[v]), npn,
+                                           sh->pnm[u], sh->pnm[v]);
+                    degenerate |= V.degenerate;
+                    store_vertex<G>(sh, s, V, pn | (u << 8) | (v << 16));
                 }
                 if(F) {
                     nV += nnew;
                     T = Tnew;
                 }
                 __syncwarp();
-                // ---- squared radius (convex_cell.cpp:1312-1330), incremental ----
-                {
-                    uint32_t rb = 0;
+            }
+            // ---- squared radius of the cell as the batch left it ----
+            {
+                const bool Aa = A && !done;
+                const uint32_t Tw = __reduce_max_sync(kFull, Aa ? T : 0u);
+                uint32_t rb = 0;
 #pragma unroll
-                    for(int r = 0; r < R; ++r) {
-                        uint32_t s = lt + G * r;
-                        if(s < T) {
-                            rb = max(rb, __float_as_uint(sh->vr[s]));
-                        }
+                for(int r = 0; r < R; ++r) {
+                    uint32_t s = lt + G * r;
+                    if(uint32_t(G * r) < Tw && Aa && s < T) {
+                        rb = max(rb, __float_as_uint(sh->vr[s]));
                     }
-                    rb = tm.max_u32(rb);
-                    if(F) {
-                        R2 = __uint_as_float(rb);
-                        bnd = sr_bound(R2);
-                    }
+                }
+                rb = tm.max_u32(rb);
+                if(Aa) {
+                    R2 = __uint_as_float(rb);
+                    bnd = sr_bound(R2);
                 }
             }
             if(A) {
@@ -968,12 +994,19 @@ __global__ void __launch_bounds__(32 * WPB, B200VOR_FUSED_MINBLOCKS) cells_fused
         used = (unsigned long long)ulo | ((unsigned long long)uhi << 32);
     }
     const uint32_t F = uint32_t(__popcll(used));
+    // foot scale -d/|n|^2 of every contributing plane, once per face: it replaces d in place
+    for(uint32_t p = lt; p < uint32_t(PC); p += G) {
+        if((used >> p) & 1ull) {
+            Plane pf = load_plane(sh->pl[p]);
+            sh->pl[p][3] = -pf.d / (pf.a * pf.a + pf.b * pf.b + pf.c * pf.c);
+        }
+    }
     {
         bool mine = false;
         for(uint32_t p = lt; p < uint32_t(PC); p += G) {
             mine = mine || (((used >> p) & 1ull) && sh->gimg[p] == kImgBox);
         }
-        if(tm.any(mine) && P.periodic && !(status & B200VOR_CELL_EMPTY)) {
+        if(tm.any(mine) && P.periodic && !(status & (B200VOR_CELL_EMPTY | B200VOR_CELL_OVERFLOW))) {
             status |= B200VOR_CELL_BOXFACE;
         }
     }
@@ -1050,7 +1083,7 @@ __global__ void __launch_bounds__(32 * WPB, B200VOR_FUSED_MINBLOCKS) cells_fused
                 Plane pf = load_plane(sh->pl[f]);
                 double cxp = uy * vz - uz * vy, cyp = uz * vx - ux * vz, czp = ux * vy - uy * vx;
                 double nc = pf.a * cxp + pf.b * cyp + pf.c * czp;
-                double inv = -pf.d / (pf.a * pf.a + pf.b * pf.b + pf.c * pf.c);
+                double inv = pf.d;   // foot scale, see above
                 double vol6 = inv * nc;
                 m6 += vol6;
                 gx += vol6 * (pf.a * inv + ux + vx);
