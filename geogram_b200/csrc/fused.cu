@@ -44,13 +44,13 @@ namespace b200vor {
 namespace {
 
 #ifndef B200VOR_FUSED_MINBLOCKS
-#define B200VOR_FUSED_MINBLOCKS 4
+#define B200VOR_FUSED_MINBLOCKS 2
 #endif
 #ifndef B200VOR_FUSED_G
 #define B200VOR_FUSED_G 16     // lanes per cell
 #endif
 #ifndef B200VOR_FUSED_WPB
-#define B200VOR_FUSED_WPB 4    // warps per block
+#define B200VOR_FUSED_WPB 8    // warps per block (8 x 2 cells share their neighbourhood in L1)
 #endif
 constexpr int NT = 48;      // cell-vertex (dual triangle) slots
 constexpr int PC = 40;      // plane slots (0..5 = clipping box)
@@ -301,7 +301,7 @@ __device__ inline double coverage2(const GridDesc& Gd, double sx, double sy, dou
     return dmin > 0.0 ? dmin * dmin : 0.0;
 }
 
-template <int G, bool FACES, int WPB>
+template <int G, bool FACES, int WPB, bool EV>
 __global__ void __launch_bounds__(32 * WPB, B200VOR_FUSED_MINBLOCKS) cells_fused_kernel(FusedParams P) {
     constexpr int TPW = 32 / G;
     constexpr int R = NT / G;
@@ -576,7 +576,9 @@ __global__ void __launch_bounds__(32 * WPB, B200VOR_FUSED_MINBLOCKS) cells_fused
                 __syncwarp();
             }
             if(sc) {
-                ++nscan;
+                if(EV) {
+                    ++nscan;
+                }
                 first = false;
                 pos = 0;
                 if(count > uint32_t(POOL)) {
@@ -677,8 +679,10 @@ __global__ void __launch_bounds__(32 * WPB, B200VOR_FUSED_MINBLOCKS) cells_fused
                     }
                 }
                 const uint32_t nt = __popc(tm.ballot(tst));
-                nP += nt;
-                nC += nt * T;
+                if(EV) {
+                    nP += nt;
+                    nC += nt * T;
+                }
             }
             uint32_t flags = tm.ballot(cuts);
             // candidates beyond the security radius end the walk (sorted: a suffix)
@@ -752,7 +756,9 @@ __global__ void __launch_bounds__(32 * WPB, B200VOR_FUSED_MINBLOCKS) cells_fused
                     if(anyunc && F) {
                         status |= B200VOR_CELL_UNCERTAIN;
                     }
-                    nC += F ? T : 0u;
+                    if(EV) {
+                        nC += F ? T : 0u;
+                    }
                 }
                 if(F && nconf == 0) {
                     F = false;   // the cell shrank since the pre-filter: no longer cut
@@ -931,7 +937,9 @@ __global__ void __launch_bounds__(32 * WPB, B200VOR_FUSED_MINBLOCKS) cells_fused
                     store_vertex<G>(sh, s, V, pn | (u << 8) | (v << 16));
                 }
                 if(F) {
-                    nV += nnew;
+                    if(EV) {
+                        nV += nnew;
+                    }
                     T = Tnew;
                 }
                 __syncwarp();
@@ -1113,7 +1121,7 @@ __global__ void __launch_bounds__(32 * WPB, B200VOR_FUSED_MINBLOCKS) cells_fused
         P.mg[3 * size_t(row) + 1] = dead ? 0.0 : sgn * gy / 24.0 + mm * si.y;
         P.mg[3 * size_t(row) + 2] = dead ? 0.0 : sgn * gz / 24.0 + mm * si.z;
         P.status[row] = uint8_t(status);
-        if(P.evcount) {
+        if(EV) {
             P.evcount[2 * size_t(row)] = min(nP, 0xffffu) | (min(nV, 0xfffu) << 16) | (min(nscan, 15u) << 28);
             P.evcount[2 * size_t(row) + 1] = min(nC, 0xfffffu) | (T << 20);
         }
@@ -1219,15 +1227,12 @@ int run_cells_fused(Ctx* c, uint32_t nq, const uint32_t* qlist, int want_faces, 
     constexpr int G = B200VOR_FUSED_G, WPB = B200VOR_FUSED_WPB, TPW = 32 / G;
     size_t smem = sizeof(TeamShared<G>) * TPW * WPB;
     uint32_t nblk = (nq + TPW * WPB - 1) / (TPW * WPB);
-    if(want_faces) {
-        B200_CUDA_CHECK(cudaFuncSetAttribute(cells_fused_kernel<G, true, WPB>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        cells_fused_kernel<G, true, WPB><<<nblk, 32 * WPB, smem, c->stream>>>(P);
-    } else {
-        B200_CUDA_CHECK(cudaFuncSetAttribute(cells_fused_kernel<G, false, WPB>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        cells_fused_kernel<G, false, WPB><<<nblk, 32 * WPB, smem, c->stream>>>(P);
-    }
+    // four instances: face lists or not, event counters (SURVEY 8(d) flop model) or not
+    void (*kern)(FusedParams) =
+        want_faces ? (collect_events ? cells_fused_kernel<G, true, WPB, true> : cells_fused_kernel<G, true, WPB, false>)
+                   : (collect_events ? cells_fused_kernel<G, false, WPB, true> : cells_fused_kernel<G, false, WPB, false>);
+    B200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    kern<<<nblk, 32 * WPB, smem, c->stream>>>(P);
     c->stats.gpu_launches++;
     B200_CUDA_CHECK(cudaGetLastError());
     return B200VOR_OK;
