@@ -27,14 +27,15 @@ EXPORTS = [
     "b200vor_version", "b200vor_last_error", "b200vor_create", "b200vor_destroy",
     "b200vor_set_domain_box", "b200vor_set_domain_periodic", "b200vor_set_points",
     "b200vor_knn", "b200vor_knn_points", "b200vor_compute_cells", "b200vor_get_cells",
-    "b200vor_get_faces", "b200vor_lloyd", "b200vor_get_stats",
+    "b200vor_get_faces", "b200vor_get_cvt", "b200vor_lloyd", "b200vor_get_stats",
     "b200vor_set_points_per_cell", "b200vor_set_stream", "b200vor_set_query_range",
 ]
 
 
 class CellParams(ctypes.Structure):
     _fields_ = [("k0", ctypes.c_uint32), ("kmax", ctypes.c_uint32),
-                ("want_faces", ctypes.c_uint32), ("mode", ctypes.c_uint32)]
+                ("want_faces", ctypes.c_uint32), ("mode", ctypes.c_uint32),
+                ("want_energy", ctypes.c_uint32)]
 
 
 class Stats(ctypes.Structure):
@@ -93,6 +94,7 @@ def load_library():
     lib.b200vor_compute_cells.argtypes = [vp, ctypes.POINTER(CellParams)]
     lib.b200vor_get_cells.argtypes = [vp, vp, vp, vp, i32]
     lib.b200vor_get_faces.argtypes = [vp, vp, vp, vp, u32, i32]
+    lib.b200vor_get_cvt.argtypes = [vp, vp, vp, ctypes.POINTER(dbl), i32]
     lib.b200vor_lloyd.argtypes = [vp, u32, ctypes.POINTER(CellParams), vp, i32]
     lib.b200vor_get_stats.argtypes = [vp, ctypes.POINTER(Stats)]
     lib.b200vor_set_points_per_cell.argtypes = [vp, dbl]
@@ -187,8 +189,9 @@ class Context(object):
         return nbr, d2
 
     # ---- cells ----
-    def compute_cells(self, k0=0, kmax=0, want_faces=False, mode=0):
-        p = CellParams(int(k0), int(kmax), 1 if want_faces else 0, int(mode))
+    def compute_cells(self, k0=0, kmax=0, want_faces=False, mode=0, want_energy=False):
+        p = CellParams(int(k0), int(kmax), 1 if want_faces else 0, int(mode),
+                       1 if want_energy else 0)
         self._check(self.lib.b200vor_compute_cells(self.h, ctypes.byref(p)))
 
     def get_cells(self):
@@ -210,16 +213,25 @@ class Context(object):
         self._check(self.lib.b200vor_get_faces(self.h, _ptr(nf), _ptr(nbr), _ptr(area), FCAP, 0))
         return nf, nbr, area
 
+    def get_cvt(self):
+        """(f_total, f_cell[n], g[n,3]) of the CVT objective (RVD.cpp:791-876); needs
+        compute_cells(want_energy=True)"""
+        f = np.zeros(self.n)
+        g = np.zeros((self.n, 3))
+        tot = ctypes.c_double(0.0)
+        self._check(self.lib.b200vor_get_cvt(self.h, _ptr(f), _ptr(g), ctypes.byref(tot), 0))
+        return tot.value, f, g
+
     def lloyd(self, iters, k0=0, kmax=0, mode=0, want_xyz=True, out=None):
         """out: optional preallocated (n,3) float64 host array (e.g. pinned) for the result"""
-        p = CellParams(int(k0), int(kmax), 0, int(mode))
+        p = CellParams(int(k0), int(kmax), 0, int(mode), 0)
         if out is None:
             out = np.zeros((self.n, 3)) if want_xyz else None
         self._check(self.lib.b200vor_lloyd(self.h, int(iters), ctypes.byref(p), _ptr(out), 0))
         return out
 
     def lloyd_device(self, iters, xyz_out_ptr=None, k0=0, kmax=0, mode=0):
-        p = CellParams(int(k0), int(kmax), 0, int(mode))
+        p = CellParams(int(k0), int(kmax), 0, int(mode), 0)
         self._check(self.lib.b200vor_lloyd(
             self.h, int(iters), ctypes.byref(p),
             _ptr(int(xyz_out_ptr)) if xyz_out_ptr else None, 1))

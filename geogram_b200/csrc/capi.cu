@@ -50,6 +50,39 @@ __global__ void gather3_kernel(const double* __restrict__ src, uint32_t stride, 
     }
 }
 
+// g_i = 2 (m_i p_i - mg_i): the per-seed sum of the gradient terms of
+// ComputeCVTFuncGradVolumetric (voronoi/RVD.cpp:861-869)
+__global__ void cvt_grad_kernel(uint32_t n, const double* __restrict__ xyz, const double* __restrict__ m,
+                                const double* __restrict__ mg, double* __restrict__ g) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if(k < 3 * n) {
+        g[k] = 2.0 * (m[k / 3] * xyz[k] - mg[k]);
+    }
+}
+
+// fixed-order sum: block b adds its contiguous slice with a fixed tree; the host adds the
+// partials in block order
+__global__ void sum_kernel(const double* __restrict__ v, uint32_t n, double* __restrict__ part) {
+    __shared__ double sm[256];
+    const uint32_t per = (n + gridDim.x - 1) / gridDim.x;
+    const uint32_t b = blockIdx.x * per, e = min(n, b + per);
+    double acc = 0.0;
+    for(uint32_t i = b + threadIdx.x; i < e; i += blockDim.x) {
+        acc += v[i];
+    }
+    sm[threadIdx.x] = acc;
+    __syncthreads();
+    for(uint32_t o = blockDim.x / 2; o > 0; o >>= 1) {
+        if(threadIdx.x < o) {
+            sm[threadIdx.x] += sm[threadIdx.x + o];
+        }
+        __syncthreads();
+    }
+    if(threadIdx.x == 0) {
+        part[blockIdx.x] = sm[0];
+    }
+}
+
 struct Timer {
     // device-side timing of a sequence of launches on the context's stream
     std::vector<cudaEvent_t> ev;
@@ -95,7 +128,7 @@ int copy_out(void* dst, const void* src, size_t bytes, int on_device, cudaStream
 }
 
 int cells_pipeline(Ctx* c, const b200vor_cell_params* params, bool collect_events) {
-    b200vor_cell_params p = {48, 384, 0, 0};
+    b200vor_cell_params p = {48, 384, 0, 0, 0};
     if(params) {
         p = *params;
     }
@@ -128,6 +161,9 @@ int cells_pipeline(Ctx* c, const b200vor_cell_params* params, bool collect_event
             return rc;
         }
     }
+    if(p.want_energy && (rc = c->energy.reserve(n))) {
+        return rc;
+    }
     if(collect_events) {
         if((rc = c->evcount.reserve(2 * size_t(n)))) {
             return rc;
@@ -156,7 +192,8 @@ int cells_pipeline(Ctx* c, const b200vor_cell_params* params, bool collect_event
     if(p.mode != 2) {
         // fused grid walk: one launch, no neighbour table (fused.cu)
         T.mark(2);
-        if((rc = run_cells_fused(c, nq, qlist, int(p.want_faces), collect_events ? 1 : 0, 0.f))) {
+        if((rc = run_cells_fused(c, nq, qlist, int(p.want_faces), collect_events ? 1 : 0, 0.f,
+                                 int(p.want_energy)))) {
             return rc;
         }
         T.mark(0);
@@ -194,7 +231,8 @@ int cells_pipeline(Ctx* c, const b200vor_cell_params* params, bool collect_event
         }
         T.mark(2);
         CellJob cj = {nq, qlist, nullptr, 2, rl, c->knn.p, c->knn_flag.p, int(p.want_faces),
-                      collect_events ? 1 : 0, int(p.mode), uint64_t(rl) >= ntotal ? 1 : 0};
+                      collect_events ? 1 : 0, int(p.mode), uint64_t(rl) >= ntotal ? 1 : 0,
+                      int(p.want_energy)};
         if((rc = run_cells(c, cj))) {
             return rc;
         }
@@ -245,6 +283,7 @@ int cells_pipeline(Ctx* c, const b200vor_cell_params* params, bool collect_event
     c->stats.ms_clip += T.sum(2);
     c->cells_valid = true;
     c->faces_valid = p.want_faces != 0;
+    c->energy_valid = p.want_energy != 0;
     return B200VOR_OK;
 }
 
@@ -314,7 +353,7 @@ void b200vor_destroy(b200vor_ctx* h) {
     c.cell_start.release(); c.perm.release(); c.scan_tmp.release(); c.sorted.release();
     c.knn.release(); c.knn_flag.release(); c.qlist.release(); c.qlist2.release(); c.qlist3.release(); c.qrows.release();
     c.counter.release(); c.m.release(); c.mg.release(); c.status.release();
-    c.nfaces.release(); c.face_nbr.release(); c.face_area.release(); c.evcount.release();
+    c.energy.release(); c.nfaces.release(); c.face_nbr.release(); c.face_area.release(); c.evcount.release();
     c.sums.release(); c.out_nbr.release(); c.out_d2.release(); c.qpts.release();
     if(c.own_stream) {
         cudaStreamDestroy(c.stream);
@@ -580,6 +619,55 @@ int b200vor_get_cells(b200vor_ctx* h, double* m, double* mg, uint8_t* status, in
     return B200VOR_OK;
 }
 
+int b200vor_get_cvt(b200vor_ctx* h, double* f_cell, double* g, double* f_total, int on_device) {
+    if(!h || !h->c.cells_valid || !h->c.energy_valid) {
+        set_error("b200vor_get_cvt: cells were not computed with want_energy=1");
+        return B200VOR_ERR_ARG;
+    }
+    Ctx* c = &h->c;
+    B200_CUDA_CHECK(cudaSetDevice(c->device));
+    int rc;
+    const uint32_t n = c->n;
+    if(f_cell && (rc = copy_out(f_cell, c->energy.p, size_t(n) * sizeof(double), on_device, c->stream))) {
+        return rc;
+    }
+    if(g) {
+        double* dg = g;
+        if(!on_device) {
+            if((rc = c->out_d2.reserve(3 * size_t(n)))) {
+                return rc;
+            }
+            dg = c->out_d2.p;
+        }
+        cvt_grad_kernel<<<(3 * n + 255) / 256, 256, 0, c->stream>>>(n, c->xyz.p, c->m.p, c->mg.p, dg);
+        c->stats.gpu_launches++;
+        B200_CUDA_CHECK(cudaGetLastError());
+        if(!on_device && (rc = copy_out(g, dg, 3 * size_t(n) * sizeof(double), 0, c->stream))) {
+            return rc;
+        }
+    }
+    if(f_total) {
+        const int nb = 128;
+        if((rc = c->sums.reserve(256))) {
+            return rc;
+        }
+        double* part = reinterpret_cast<double*>(c->sums.p);
+        sum_kernel<<<nb, 256, 0, c->stream>>>(c->energy.p, n, part);
+        c->stats.gpu_launches++;
+        B200_CUDA_CHECK(cudaGetLastError());
+        double hp[nb];
+        B200_CUDA_CHECK(cudaMemcpyAsync(hp, part, sizeof(hp), cudaMemcpyDeviceToHost, c->stream));
+        B200_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        double t = 0.0;
+        for(int b = 0; b < nb; ++b) {
+            t += hp[b];
+        }
+        *f_total = t;
+    }
+    B200_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return B200VOR_OK;
+}
+
 int b200vor_get_faces(b200vor_ctx* h, uint32_t* nfaces, uint32_t* face_nbr, double* face_area,
                       uint32_t fcap, int on_device) {
     if(!h || !h->c.faces_valid) {
@@ -611,11 +699,12 @@ int b200vor_lloyd(b200vor_ctx* h, uint32_t iters, const b200vor_cell_params* par
     }
     Ctx* c = &h->c;
     B200_CUDA_CHECK(cudaSetDevice(c->device));
-    b200vor_cell_params p = {48, 384, 0, 0};
+    b200vor_cell_params p = {48, 384, 0, 0, 0};
     if(params) {
         p = *params;
     }
     p.want_faces = 0;
+    p.want_energy = 0;
     int rc;
     c->stats.ms_knn = c->stats.ms_clip = 0.f;
     if(c->grid_dirty) {

@@ -67,6 +67,7 @@ struct CellParams {
     CellJob job;
     double* m;
     double* mg;
+    double* energy;
     uint8_t* status;
     uint32_t* nfaces;
     uint32_t* face_nbr;
@@ -416,7 +417,8 @@ __device__ inline void integrate(WarpCell<S>& C, const CellParams& P, const Seed
         }
     }
     __syncwarp();
-    double m6 = 0.0, gx = 0.0, gy = 0.0, gz = 0.0;
+    double m6 = 0.0, gx = 0.0, gy = 0.0, gz = 0.0, e6 = 0.0;
+    const bool want_e = P.energy != nullptr;
     double ncr[S][3];   // n_f . (u x v) per outgoing directed edge (for the areas)
 #pragma unroll
     for(int s = 0; s < S; ++s) {
@@ -440,9 +442,16 @@ __device__ inline void integrate(WarpCell<S>& C, const CellParams& P, const Seed
                 double inv = -d / (a * a + b * b + c * c);
                 double vol6 = inv * nc;                  // foot . (u x v), foot = inv * n
                 m6 += vol6;
-                gx += vol6 * (a * inv + ux + vx);
-                gy += vol6 * (b * inv + uy + vy);
-                gz += vol6 * (c * inv + uz + vz);
+                const double fx = a * inv, fy = b * inv, fz = c * inv;
+                gx += vol6 * (fx + ux + vx);
+                gy += vol6 * (fy + uy + vy);
+                gz += vol6 * (fz + uz + vz);
+                if(want_e) {   // RVD.cpp:846-857 on the simplex (seed, foot, u, v)
+                    double q = (fx * fx + fy * fy + fz * fz) + (ux * ux + uy * uy + uz * uz) +
+                               (vx * vx + vy * vy + vz * vz) + (fx * ux + fy * uy + fz * uz) +
+                               (ux * vx + uy * vy + uz * vz) + (vx * fx + vy * fy + vz * fz);
+                    e6 += vol6 * q;
+                }
                 ncr[s][l] = nc;
             }
         }
@@ -451,6 +460,9 @@ __device__ inline void integrate(WarpCell<S>& C, const CellParams& P, const Seed
     gx = warp_sum(gx);
     gy = warp_sum(gy);
     gz = warp_sum(gz);
+    if(want_e) {
+        e6 = warp_sum(e6);
+    }
     double sgn = m6 < 0.0 ? -1.0 : 1.0;
     double mass = sgn * m6 / 6.0;
     if(lane == 0) {
@@ -460,6 +472,9 @@ __device__ inline void integrate(WarpCell<S>& C, const CellParams& P, const Seed
         P.mg[3 * size_t(row)] = dead ? 0.0 : sgn * gx / 24.0 + mm * si.x;
         P.mg[3 * size_t(row) + 1] = dead ? 0.0 : sgn * gy / 24.0 + mm * si.y;
         P.mg[3 * size_t(row) + 2] = dead ? 0.0 : sgn * gz / 24.0 + mm * si.z;
+        if(want_e) {
+            P.energy[row] = dead ? 0.0 : sgn * e6 / 60.0;
+        }
     }
     if(FACES) {
         unsigned long long used = C.used_planes();
@@ -836,6 +851,7 @@ int run_cells(Ctx* c, const CellJob& job) {
     P.job = job;
     P.m = c->m.p;
     P.mg = c->mg.p;
+    P.energy = job.want_energy ? c->energy.p : nullptr;
     P.status = c->status.p;
     P.nfaces = c->nfaces.p;
     P.face_nbr = c->face_nbr.p;

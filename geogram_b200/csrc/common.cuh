@@ -123,6 +123,8 @@ struct Ctx {
 
     // cell outputs, user order
     DevBuf<double> m, mg;
+    DevBuf<double> energy;     // per-cell integral of |x - p_i|^2 (only with want_energy)
+    bool energy_valid = false;
     DevBuf<uint8_t> status;
     DevBuf<uint32_t> nfaces, face_nbr;
     DevBuf<double> face_area;
@@ -166,11 +168,12 @@ struct CellJob {
     int collect_events;
     int mode;
     int all_offered;         // 1: every row lists all other seeds (k >= n-1)
+    int want_energy;
 };
 int run_cells(Ctx* c, const CellJob& job);
 // fused.cu
 int run_cells_fused(Ctx* c, uint32_t nq, const uint32_t* qlist, int want_faces,
-                    int collect_events, float target);
+                    int collect_events, float target, int want_energy);
 int compact_failed(Ctx* c, const uint32_t* qlist_in, uint32_t nq_in, uint32_t* qlist_out,
                    uint32_t* rows_out, uint32_t* count_out_host, uint8_t mask);
 int lloyd_update(Ctx* c);

@@ -77,6 +77,7 @@ struct FusedParams {
     const uint32_t* qlist;   // grid-order indices of the cells to compute, or NULL (= all)
     double* m;
     double* mg;
+    double* energy;          // NULL, or the per-cell integral of |x - seed|^2
     uint8_t* status;
     uint32_t* nfaces;
     uint32_t* face_nbr;
@@ -1062,7 +1063,8 @@ __global__ void __launch_bounds__(32 * WPB, B200VOR_FUSED_MINBLOCKS) cells_fused
         }
     }
     __syncwarp();
-    double m6 = 0.0, gx = 0.0, gy = 0.0, gz = 0.0;
+    double m6 = 0.0, gx = 0.0, gy = 0.0, gz = 0.0, e6 = 0.0;
+    const bool want_e = P.energy != nullptr;
     double ncr[FACES ? R : 1][3];
 #pragma unroll
     for(int r = 0; r < R; ++r) {
@@ -1094,9 +1096,18 @@ __global__ void __launch_bounds__(32 * WPB, B200VOR_FUSED_MINBLOCKS) cells_fused
                 double inv = pf.d;   // foot scale, see above
                 double vol6 = inv * nc;
                 m6 += vol6;
-                gx += vol6 * (pf.a * inv + ux + vx);
-                gy += vol6 * (pf.b * inv + uy + vy);
-                gz += vol6 * (pf.c * inv + uz + vz);
+                const double fx = pf.a * inv, fy = pf.b * inv, fz = pf.c * inv;   // foot of the face plane
+                gx += vol6 * (fx + ux + vx);
+                gy += vol6 * (fy + uy + vy);
+                gz += vol6 * (fz + uz + vz);
+                if(want_e) {
+                    // RVD.cpp:846-857 on the simplex (seed, foot, u, v), seed at the origin:
+                    // U.U + V.V + W.W + U.V + V.W + W.U
+                    double q = (fx * fx + fy * fy + fz * fz) + (ux * ux + uy * uy + uz * uz) +
+                               (vx * vx + vy * vy + vz * vz) + (fx * ux + fy * uy + fz * uz) +
+                               (ux * vx + uy * vy + uz * vz) + (vx * fx + vy * fy + vz * fz);
+                    e6 += vol6 * q;
+                }
                 if(FACES) {
                     ncr[FACES ? r : 0][l] = nc;
                 }
@@ -1107,6 +1118,9 @@ __global__ void __launch_bounds__(32 * WPB, B200VOR_FUSED_MINBLOCKS) cells_fused
     gx = tm.sum(gx);
     gy = tm.sum(gy);
     gz = tm.sum(gz);
+    if(want_e) {
+        e6 = tm.sum(e6);
+    }
     // Euler's relation T = 2F - 4 and every directed edge has its twin
     const bool consistent = !tm.any(!ok) && !tm.any(degenerate) && (T + 4 == 2 * F);
     if(T > 0 && tableok && !consistent) {
@@ -1121,6 +1135,9 @@ __global__ void __launch_bounds__(32 * WPB, B200VOR_FUSED_MINBLOCKS) cells_fused
         P.mg[3 * size_t(row) + 1] = dead ? 0.0 : sgn * gy / 24.0 + mm * si.y;
         P.mg[3 * size_t(row) + 2] = dead ? 0.0 : sgn * gz / 24.0 + mm * si.z;
         P.status[row] = uint8_t(status);
+        if(want_e) {
+            P.energy[row] = dead ? 0.0 : sgn * e6 / 60.0;
+        }
         if(EV) {
             P.evcount[2 * size_t(row)] = min(nP, 0xffffu) | (min(nV, 0xfffu) << 16) | (min(nscan, 15u) << 28);
             P.evcount[2 * size_t(row) + 1] = min(nC, 0xfffffu) | (T << 20);
@@ -1193,7 +1210,7 @@ __global__ void __launch_bounds__(32 * WPB, B200VOR_FUSED_MINBLOCKS) cells_fused
 }  // namespace
 
 int run_cells_fused(Ctx* c, uint32_t nq, const uint32_t* qlist, int want_faces, int collect_events,
-                    float target) {
+                    float target, int want_energy) {
     if(nq == 0) {
         return B200VOR_OK;
     }
@@ -1214,6 +1231,7 @@ int run_cells_fused(Ctx* c, uint32_t nq, const uint32_t* qlist, int want_faces, 
     P.qlist = qlist;
     P.m = c->m.p;
     P.mg = c->mg.p;
+    P.energy = want_energy ? c->energy.p : nullptr;
     P.status = c->status.p;
     P.nfaces = c->nfaces.p;
     P.face_nbr = c->face_nbr.p;

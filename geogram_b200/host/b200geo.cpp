@@ -289,6 +289,23 @@ void CentroidalVoronoiTesselation::lock_point(index_t i) {
     point_is_locked_[i] = true;
 }
 
+void CentroidalVoronoiTesselation::funcgrad(index_t n, double* x, double& f, double* g) {
+    const index_t nb = n / 3;
+    check(b200vor_set_points(ctx_, nb, x, 3, nullptr, 0), "funcgrad (set_points)");
+    b200vor_cell_params p;
+    memset(&p, 0, sizeof(p));
+    p.want_energy = 1;
+    check(b200vor_compute_cells(ctx_, &p), "funcgrad (compute_cells)");
+    check(b200vor_get_cvt(ctx_, nullptr, g, &f, 0), "funcgrad (get_cvt)");
+    if(!point_is_locked_.empty()) {
+        for(index_t i = 0; i < nb && i < index_t(point_is_locked_.size()); ++i) {
+            if(point_is_locked_[i]) {
+                g[3 * size_t(i)] = g[3 * size_t(i) + 1] = g[3 * size_t(i) + 2] = 0.0;
+            }
+        }
+    }
+}
+
 void CentroidalVoronoiTesselation::Lloyd_iterations(index_t nb_iter) {
     const index_t n = nb_points();
     if(n == 0 || nb_iter == 0) {

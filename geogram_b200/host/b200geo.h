@@ -166,6 +166,12 @@ public:
     bool point_is_locked(index_t i) const { return !point_is_locked_.empty() && point_is_locked_[i]; }
     /* p_j <- mg_j / m_j where m_j > 1e-30 and j is not locked (CVT.cpp:150-163) */
     void Lloyd_iterations(index_t nb_iter);
+    /* CVT objective and gradient at x (n = 3 * nb_points doubles), the callback
+       Newton_iterations() hands to its optimizer (CVT.cpp:323-341):
+       f = sum_i integral over cell i of |y - x_i|^2, g_i = 2 (m_i x_i - mg_i)
+       (ComputeCVTFuncGradVolumetric, RVD.cpp:791-876); locked points get g = 0
+       (constrain_points, CVT.cpp:309-321).  Security-radius checking is always on. */
+    void funcgrad(index_t n, double* x, double& f, double* g);
 
 private:
     b200vor_ctx* ctx_;

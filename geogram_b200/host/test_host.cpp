@@ -157,6 +157,29 @@ int main() {
         v1 += (c2.volume(c) - 1.0 / n) * (c2.volume(c) - 1.0 / n);
     }
     EXPECT(v1 < 0.6 * v0);
+    // ---- funcgrad (CVT.cpp:323-341): f decreases under Lloyd, g = 0 on the locked point, and
+    //      a finite difference of f along -g matches |g|^2 (the CVT gradient formula)
+    {
+        std::vector<double> x(pts), g(3 * size_t(n)), x2(3 * size_t(n)), g2(3 * size_t(n));
+        double f0 = 0, f1 = 0, f2 = 0;
+        cvt.funcgrad(3 * n, x.data(), f0, g.data());
+        EXPECT(g[0] == 0.0 && g[1] == 0.0 && g[2] == 0.0);
+        std::vector<double> xr(cvt.embedding(0), cvt.embedding(0) + 3 * size_t(n));
+        cvt.funcgrad(3 * n, xr.data(), f1, g2.data());
+        EXPECT(f0 > 0 && f1 < f0);
+        cvt.unlock_all_points();
+        cvt.funcgrad(3 * n, x.data(), f0, g.data());
+        double gg = 0;
+        for(size_t k = 0; k < g.size(); ++k) {
+            gg += g[k] * g[k];
+        }
+        const double h = 1.0;   // displacement h*|g_i| ~ 1e-5 of a 0.06 cell: linear regime
+        for(size_t k = 0; k < g.size(); ++k) {
+            x2[k] = x[k] - h * g[k];
+        }
+        cvt.funcgrad(3 * n, x2.data(), f2, g2.data());
+        EXPECT(fabs((f0 - f2) / h - gg) < 0.05 * gg);
+    }
     printf(fails ? "host test: %d FAILURES\n" : "host test: ok\n", fails);
     return fails ? 1 : 0;
 }

@@ -27,6 +27,7 @@
  *   b200vor_get_cells        RestrictedVoronoiDiagram::compute_centroids (mg, m)
  *                                                                   voronoi/RVD.h:284-290
  *   b200vor_get_faces        ConvexCell::v_global_index / facet_area voronoi/convex_cell.h:463, convex_cell.cpp:1160
+ *   b200vor_get_cvt          ComputeCVTFuncGradVolumetric (f, g)    voronoi/RVD.cpp:791-876
  *   b200vor_lloyd            CentroidalVoronoiTesselation::Lloyd_iterations
  *                                                                   voronoi/CVT.cpp:133-169
  */
@@ -72,6 +73,8 @@ typedef struct b200vor_cell_params {
                                  OVERFLOW are re-done by the kNN-table pipeline
                              1 = fused grid walk only (flags are left on the cells)
                              2 = kNN table -> clipper (re-launch failing cells with larger k) */
+    uint32_t want_energy; /* 1: also integrate |x - p_i|^2 over every cell (CVT energy) for
+                             b200vor_get_cvt                                               */
 } b200vor_cell_params;
 
 typedef struct b200vor_stats {
@@ -125,6 +128,14 @@ int b200vor_get_cells(b200vor_ctx* ctx, double* m, double* mg, uint8_t* status, 
 /* nfaces[n], face_nbr[n*fcap] (ascending ids), face_area[n*fcap] (may be NULL) */
 int b200vor_get_faces(b200vor_ctx* ctx, uint32_t* nfaces, uint32_t* face_nbr,
                       double* face_area, uint32_t fcap, int on_device);
+
+/* CVT objective of the last b200vor_compute_cells(want_energy=1)
+ * (ComputeCVTFuncGradVolumetric, voronoi/RVD.cpp:791-876, summed per seed):
+ *   f_cell[n]  f_i = integral over cell i of |x - p_i|^2   (sum of the functor's fi)
+ *   g[3n]      g_i = 2 (m_i p_i - mg_i)                    (sum of the functor's gi)
+ *   f_total    sum of f_i in a fixed order (deterministic)
+ * any output may be NULL; f_total is always a host pointer */
+int b200vor_get_cvt(b200vor_ctx* ctx, double* f_cell, double* g, double* f_total, int on_device);
 
 /* ---- Lloyd relaxation: iters x (grid, cells, p <- mg/m, periodic wrap) ---- */
 /* xyz_out (n x 3, may be NULL) receives the relaxed points */

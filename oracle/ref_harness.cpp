@@ -240,6 +240,94 @@ int georef_cells_delaunay(
 }
 
 /*
+ * CVT energy per cell on the exact cells of oracle A: f_i = sum over the integration
+ * simplices (seed, p1, p2, p3) of the cell of
+ *     (mi/10) * (U.U + V.V + W.W + U.V + V.W + W.U),  U = p1-p0, V = p2-p0, W = p3-p0,
+ * the formula of ComputeCVTFuncGradVolumetric (voronoi/RVD.cpp:846-857); the simplices are
+ * the fans of the cell facets as ConvexCell::compute_mg walks them (convex_cell.cpp:1267-1307),
+ * with the seed as apex.  The gradient of that functor is 2*(m_i p_i - mg_i) and needs no
+ * extra output.  Returns 1 if has_empty_cells().
+ */
+int georef_cvt_energy(
+    uint32_t n, const double* xyz, const double* w, int periodic, double period,
+    double* energy
+) {
+    georef_init(0);
+    GEO::SmartPointer<GEO::PeriodicDelaunay3d> del =
+        new GEO::PeriodicDelaunay3d(periodic != 0, period);
+    if(!periodic) {
+        del->set_keeps_infinite(true);
+    }
+    del->set_stores_cicl(false);
+    del->set_vertices(n, xyz);
+    if(w != nullptr) {
+        del->set_weights(w);
+    }
+    del->compute();
+    if(del->has_empty_cells()) {
+        return 1;
+    }
+    GEO::parallel_for_slice(0, n,
+        [&](GEO::index_t b, GEO::index_t e) {
+            VBW::ConvexCell C;
+            GEO::PeriodicDelaunay3d::IncidentTetrahedra W;
+            for(GEO::index_t v = b; v < e; ++v) {
+                del->copy_Laguerre_cell_from_Delaunay(v, C, W);
+                if(!periodic) {
+                    C.clip_by_plane(VBW::vec4( 1.0, 0.0, 0.0, 0.0), BOX_ID + 0);
+                    C.clip_by_plane(VBW::vec4(-1.0, 0.0, 0.0, 1.0), BOX_ID + 1);
+                    C.clip_by_plane(VBW::vec4( 0.0, 1.0, 0.0, 0.0), BOX_ID + 2);
+                    C.clip_by_plane(VBW::vec4( 0.0,-1.0, 0.0, 1.0), BOX_ID + 3);
+                    C.clip_by_plane(VBW::vec4( 0.0, 0.0, 1.0, 0.0), BOX_ID + 4);
+                    C.clip_by_plane(VBW::vec4( 0.0, 0.0,-1.0, 1.0), BOX_ID + 5);
+                }
+                C.compute_geometry();
+                const double* p0 = xyz + 3 * size_t(v);
+                double f = 0.0;
+                for(VBW::index_t lv = 1; lv < C.nb_v(); ++lv) {
+                    VBW::index_t tfirst = C.vertex_triangle(lv);
+                    if(tfirst == VBW::END_OF_LIST) {
+                        continue;
+                    }
+                    VBW::ushort t1t2[2];
+                    VBW::index_t cur = 0, t = tfirst;
+                    do {
+                        if(cur < 2) {
+                            t1t2[cur] = VBW::ushort(t);
+                        } else {
+                            VBW::vec3 P[3] = {C.triangle_point(t1t2[0]), C.triangle_point(t1t2[1]),
+                                              C.triangle_point(VBW::ushort(t))};
+                            double U[3][3];
+                            for(int k = 0; k < 3; ++k) {
+                                U[k][0] = P[k].x - p0[0];
+                                U[k][1] = P[k].y - p0[1];
+                                U[k][2] = P[k].z - p0[2];
+                            }
+                            double det = U[0][0] * (U[1][1] * U[2][2] - U[1][2] * U[2][1])
+                                       - U[0][1] * (U[1][0] * U[2][2] - U[1][2] * U[2][0])
+                                       + U[0][2] * (U[1][0] * U[2][1] - U[1][1] * U[2][0]);
+                            double mi = std::fabs(det) / 6.0;
+                            double fi = 0.0;
+                            for(int c = 0; c < 3; ++c) {
+                                double Uc = U[0][c], Vc = U[1][c], Wc = U[2][c];
+                                fi += Uc * Uc + Vc * Vc + Wc * Wc;
+                                fi += Uc * Vc + Vc * Wc + Wc * Uc;
+                            }
+                            f += fi * (mi / 10.0);
+                            t1t2[1] = VBW::ushort(t);
+                        }
+                        ++cur;
+                        VBW::index_t le = C.triangle_find_vertex(t, lv);
+                        t = C.triangle_adjacent(t, (le + 1) % 3);
+                    } while(t != tfirst);
+                }
+                energy[v] = f;
+            }
+        });
+    return 0;
+}
+
+/*
  * Oracle B ("same algorithm").  Box = [box[0..2], box[3..5]].  k0 = initial
  * neighbour count (reference default 20, delaunay_nn.cpp:49); growth k += k/8
  * (k > 8) else k++, capped at min(kcap, n-1); each growth re-queries the kd-tree

@@ -47,6 +47,7 @@
 namespace {
 
 int g_threads = 0;
+double* g_energy = nullptr;   /* vo_set_energy_output */
 
 inline double sq(double x) { return x * x; }
 
@@ -504,8 +505,15 @@ struct DualCell {
     /* convex_cell.cpp:1267-1307 (mass, mass*centroid) and :1160-1191 (areas).
      * ids/areas: contributing planes sorted by global id.  Returns #faces,
      * nI = number of integration tetrahedra. */
+    /* seed/energy (optional): CVT energy of the cell, the integral of |x - seed|^2
+     * (voronoi/RVD.cpp:846-857 restated for a tetrahedron that does not have the
+     * seed as a vertex: vol/10 * (sum_i q_i.q_i + sum_{i<j} q_i.q_j), q_i = v_i - seed) */
     uint32_t integrate(double& m, double* mg, uint32_t fcap, uint32_t* ids,
-                       double* areas, uint64_t& nI) const {
+                       double* areas, uint64_t& nI, const double* seed = nullptr,
+                       double* energy = nullptr) const {
+        if(energy) {
+            *energy = 0.0;
+        }
         m = 0.0;
         mg[0] = mg[1] = mg[2] = 0.0;
         std::vector<double> P(3 * tri.size());
@@ -544,6 +552,18 @@ struct DualCell {
                     m += vol;
                     for(int k = 0; k < 3; ++k) {
                         mg[k] += vol * (o[k] + a[k] + b[k] + c[k]) / 4.0;
+                    }
+                    if(energy) {
+                        const double* q4[4] = {o, a, b, c};
+                        double e = 0.0;
+                        for(int i = 0; i < 4; ++i) {
+                            for(int j = i; j < 4; ++j) {
+                                for(int k = 0; k < 3; ++k) {
+                                    e += (q4[i][k] - seed[k]) * (q4[j][k] - seed[k]);
+                                }
+                            }
+                        }
+                        *energy += vol / 10.0 * e;
                     }
                     ++nI;
                 }
@@ -587,6 +607,7 @@ int n_threads() {
 extern "C" {
 
 void vo_set_num_threads(int nthreads) { g_threads = nthreads; }
+void vo_set_energy_output(double* energy) { g_energy = energy; }
 int vo_num_threads(void) { return n_threads(); }
 
 int vo_knn(uint32_t n, const double* xyz, uint32_t k, uint32_t* nbr, double* d2) {
@@ -723,7 +744,11 @@ int vo_cells(uint32_t n, const double* xyz, const double* w, int periodic,
             double areas[256];
             uint64_t nI = 0;
             double mm, g[3];
-            uint32_t nf = C.integrate(mm, g, 256, ids, areas, nI);
+            double en = 0.0;
+            uint32_t nf = C.integrate(mm, g, 256, ids, areas, nI, pi, g_energy ? &en : nullptr);
+            if(g_energy) {
+                g_energy[i] = (fl & VO_FLAG_EMPTY) ? 0.0 : en;
+            }
             for(uint32_t f = 0; f < std::min(nf, 256u); ++f) {
                 if(periodic && ids[f] >= VO_BOX_ID) {
                     fl |= VO_FLAG_BOXFACE;

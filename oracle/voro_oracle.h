@@ -58,6 +58,11 @@ int vo_cells(uint32_t n, const double* xyz, const double* w,
              uint32_t* nfaces, uint32_t* face_nbr, double* face_area, uint32_t fcap,
              uint32_t* kstop, uint32_t* flags, double* stats);
 
+/* Optional extra output of the next vo_cells() calls: energy[n] receives the CVT energy of
+ * every cell, the integral of |x - seed_i|^2 over the cell (the per-cell share of f in
+ * ComputeCVTFuncGradVolumetric, voronoi/RVD.cpp:791-876).  NULL switches it off. */
+void vo_set_energy_output(double* energy);
+
 /* One Lloyd update: xyz_out = mg/m where m > 1e-30, else unchanged; periodic wrap. */
 int vo_lloyd_update(uint32_t n, const double* xyz, const double* m, const double* mg,
                     int periodic, double period, double* xyz_out);

@@ -84,5 +84,23 @@ def main():
     print("lloyd2_periodic_3000.npz")
 
 
+def cvt_energy():
+    """CVT objective (ComputeCVTFuncGradVolumetric, RVD.cpp:791-876) on the exact cells of the
+    unmodified reference: f_i per cell (georef_cvt_energy) and g_i = 2 (m_i p_i - mg_i) from
+    the reference's own compute_mg."""
+    R = oracles.Reference()
+    xyz = oracles.uniform_seeds(3000, 12345)
+    for periodic, tag in ((False, "box"), (True, "periodic")):
+        A = R.cells_delaunay(xyz, periodic=periodic)
+        f = R.cvt_energy(xyz, periodic=periodic)
+        g = 2.0 * (A.m[:, None] * xyz - A.mg)
+        np.savez_compressed(os.path.join(HERE, "cvt_energy_%s_3000.npz" % tag), xyz=xyz, f_cell=f, g=g)
+        print("cvt_energy_%s_3000.npz f=%.15e" % (tag, f.sum()))
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "cvt":
+        cvt_energy()
+    else:
+        main()
+        cvt_energy()

@@ -91,19 +91,22 @@ class Port(object):
         return nbr, d2
 
     def cells(self, xyz, w=None, periodic=False, period=1.0, box=UNIT_BOX,
-              k0=20, kcap=1000, fcap=64, areas=False):
+              k0=20, kcap=1000, fcap=64, areas=False, energy=False):
         xyz = np.ascontiguousarray(xyz, np.float64)
         n = xyz.shape[0]
         if w is not None:
             w = np.ascontiguousarray(w, np.float64)
         box = np.ascontiguousarray(box, np.float64)
         R = CellResult(n, fcap, areas)
+        R.energy = np.zeros(n) if energy else None
+        self.lib.vo_set_energy_output(_p(R.energy, _cd))
         r = self.lib.vo_cells(
             ctypes.c_uint32(n), _p(xyz, _cd), _p(w, _cd), int(periodic),
             ctypes.c_double(period), _p(box, _cd), ctypes.c_uint32(k0),
             ctypes.c_uint32(kcap), _p(R.m, _cd), _p(R.mg, _cd), _p(R.nfaces, _cu),
             _p(R.face_nbr, _cu), _p(R.face_area, _cd), ctypes.c_uint32(fcap),
             _p(R.kstop, _cu), _p(R.flags, _cu), _p(R.stats, _cd))
+        self.lib.vo_set_energy_output(None)
         assert r == 0
         return R
 
@@ -159,6 +162,17 @@ class Reference(object):
             _p(R.nfaces, _cu), _p(R.face_nbr, _cu), _p(R.face_area, _cd),
             ctypes.c_uint32(fcap), _p(R.times, _cd))
         return R if r == 0 else None
+
+    def cvt_energy(self, xyz, w=None, periodic=False, period=1.0):
+        """Per-cell CVT energy on the exact cells (RVD.cpp:846-857).  None if empty cells."""
+        xyz = np.ascontiguousarray(xyz, np.float64)
+        n = xyz.shape[0]
+        if w is not None:
+            w = np.ascontiguousarray(w, np.float64)
+        f = np.zeros(n)
+        r = self.lib.georef_cvt_energy(ctypes.c_uint32(n), _p(xyz, _cd), _p(w, _cd), int(periodic),
+                                       ctypes.c_double(period), _p(f, _cd))
+        return f if r == 0 else None
 
     def cells_knn(self, xyz, w=None, box=UNIT_BOX, k0=20, kcap=1000, exact=True,
                   fcap=64, areas=False):

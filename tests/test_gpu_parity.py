@@ -5,11 +5,13 @@ seeded inputs, (3) size-independent properties at BASELINE sizes.
 Tolerances (BASELINE.json north_star): face connectivity bit-exact; per-cell volume and
 centroid relative 1e-6 (the tests use 1e-9: both sides are fp64); total volume 1e-9.
 """
+import os
+
 import numpy as np
 import pytest
 
 import oracles
-from conftest import Golden
+from conftest import GOLDEN as GOLD, Golden
 
 pytestmark = pytest.mark.gpu
 
@@ -205,6 +207,42 @@ def test_laguerre_large_weights_on_relaxed_seeds(Context, port):
     assert ((R.status & ~np.uint8(4)) == 0).all()
     check(R, O)
     assert abs(R.m.sum() - 1.0) < SUM_TOL
+
+
+# ---------------------------------------------------------------- CVT objective (a17)
+@pytest.mark.parametrize("periodic", [False, True])
+def test_cvt_energy_and_gradient(Context, port, periodic):
+    """f_i = integral of |x - p_i|^2 over the cell and g_i = 2 (m_i p_i - mg_i)
+    (ComputeCVTFuncGradVolumetric, RVD.cpp:791-876) against the golden values generated
+    from the unmodified reference, and against the oracle port at 100k seeds; the total is
+    a fixed-order sum (bitwise reproducible)."""
+    G = np.load(os.path.join(GOLD, "cvt_energy_%s_3000.npz" % ("periodic" if periodic else "box")))
+    ctx = Context(0)
+    if periodic:
+        ctx.set_domain_periodic(1.0)
+    ctx.set_points(G["xyz"])
+    ctx.compute_cells(want_energy=True)
+    f, fc, g = ctx.get_cvt()
+    assert np.all(np.abs(fc - G["f_cell"]) <= VOL_RTOL * G["f_cell"])
+    assert abs(f - G["f_cell"].sum()) <= 1e-9 * f
+    assert np.abs(g - G["g"]).max() <= 1e-9 * np.abs(G["g"]).max()
+    ctx.compute_cells(want_energy=True, mode=2)       # the kNN-table pipeline integrates it too
+    f2, fc2, _ = ctx.get_cvt()
+    assert np.all(np.abs(fc2 - G["f_cell"]) <= VOL_RTOL * G["f_cell"])
+    n = 100000
+    xyz = oracles.uniform_seeds(n, 777)
+    O = port.cells(xyz, periodic=periodic, energy=True)
+    ctx.set_points(xyz)
+    ctx.compute_cells(want_energy=True)
+    fa, fca, ga = ctx.get_cvt()
+    m, mg, status = ctx.get_cells()
+    assert (status == 0).all()
+    assert np.all(np.abs(fca - O.energy) <= VOL_RTOL * O.energy)
+    assert np.abs(ga - 2.0 * (O.m[:, None] * xyz - O.mg)).max() <= 1e-9 * np.abs(ga).max()
+    ctx.compute_cells(want_energy=True)
+    fb, _, _ = ctx.get_cvt()
+    assert fa == fb
+    ctx.close()
 
 
 # ---------------------------------------------------------------- the two cell pipelines

@@ -77,6 +77,19 @@ def test_cells_clustered_golden(port):
     assert abs(R.m.sum() - 1.0) < 1e-12
 
 
+@pytest.mark.parametrize("periodic", [False, True])
+def test_cvt_energy_golden(port, periodic):
+    """the port's own tetrahedra (general 4-vertex second-moment formula) against the
+    reference-derived golden values of RVD.cpp:846-857"""
+    import os
+    from conftest import GOLDEN
+    G = np.load(os.path.join(GOLDEN, "cvt_energy_%s_3000.npz" % ("periodic" if periodic else "box")))
+    A = port.cells(G["xyz"], periodic=periodic, energy=True)
+    assert np.all(np.abs(A.energy - G["f_cell"]) <= 1e-10 * G["f_cell"])
+    g = 2.0 * (A.m[:, None] * G["xyz"] - A.mg)
+    assert np.abs(g - G["g"]).max() <= 1e-10 * np.abs(G["g"]).max()
+
+
 def test_lloyd_golden(port):
     d = np.load(oracles.ROOT + "/tests/golden/lloyd2_periodic_3000.npz")
     x = d["xyz0"]
