@@ -193,7 +193,7 @@ int cells_pipeline(Ctx* c, const b200vor_cell_params* params, bool collect_event
         // fused grid walk: one launch, no neighbour table (fused.cu)
         T.mark(2);
         if((rc = run_cells_fused(c, nq, qlist, int(p.want_faces), collect_events ? 1 : 0, 0.f,
-                                 int(p.want_energy)))) {
+                                 int(p.want_energy), 0))) {
             return rc;
         }
         T.mark(0);
@@ -204,19 +204,33 @@ int cells_pipeline(Ctx* c, const b200vor_cell_params* params, bool collect_event
         if(p.mode == 1) {
             nq = 0;
         } else {
-            // the cells it could not finish inside its fixed capacities go through the
-            // kNN-table pipeline below
-            if((rc = c->qlist.reserve(nq)) || (rc = c->qlist2.reserve(nq))) {
-                return rc;
+            // the cells it could not finish inside its fixed capacities are re-done by the
+            // large-cell instance of the same kernel (one warp per cell, 128 vertices / 64
+            // planes); what that leaves goes through the kNN-table pipeline below
+            for(int big = 1; big >= 0 && nq > 0; --big) {
+                if((rc = c->qlist.reserve(nq)) || (rc = c->qlist2.reserve(nq))) {
+                    return rc;
+                }
+                uint32_t* out = (qlist == c->qlist.p) ? c->qlist2.p : c->qlist.p;
+                uint32_t nfail = 0;
+                if((rc = compact_failed(c, qlist, nq, out, nullptr, &nfail,
+                                        B200VOR_CELL_UNCERTIFIED | B200VOR_CELL_OVERFLOW))) {
+                    return rc;
+                }
+                qlist = out;
+                nq = nfail;
+                if(big && nq > 0) {
+                    T.mark(2);
+                    if((rc = run_cells_fused(c, nq, qlist, int(p.want_faces), collect_events ? 1 : 0, 0.f,
+                                             int(p.want_energy), 1))) {
+                        return rc;
+                    }
+                    T.mark(0);
+                    c->stats.n_pass[pass0] = nq;
+                    c->stats.k_pass[pass0] = 0;
+                    c->stats.passes = ++pass0;
+                }
             }
-            uint32_t* out = (qlist == c->qlist.p) ? c->qlist2.p : c->qlist.p;
-            uint32_t nfail = 0;
-            if((rc = compact_failed(c, qlist, nq, out, nullptr, &nfail,
-                                    B200VOR_CELL_UNCERTIFIED | B200VOR_CELL_OVERFLOW))) {
-                return rc;
-            }
-            qlist = out;
-            nq = nfail;
         }
     }
     for(int pass = pass0; pass < 8 && nq > 0; ++pass) {
@@ -350,6 +364,7 @@ void b200vor_destroy(b200vor_ctx* h) {
     cudaSetDevice(c.device);
     cudaStreamSynchronize(c.stream);
     c.xyz.release(); c.wgt.release(); c.cellid.release(); c.rank.release();
+    c.sub.release(); c.vstart.release(); c.vcount.release();
     c.cell_start.release(); c.perm.release(); c.scan_tmp.release(); c.sorted.release();
     c.knn.release(); c.knn_flag.release(); c.qlist.release(); c.qlist2.release(); c.qlist3.release(); c.qrows.release();
     c.counter.release(); c.m.release(); c.mg.release(); c.status.release();

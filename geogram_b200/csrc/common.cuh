@@ -32,7 +32,15 @@ struct GridDesc {
     int periodic;
     double period;
     uint32_t ncell;
+    // two-level grid (clustered seeds): a bin with more than kDenseBin seeds carries its own
+    // s x s x s sub-grid, s = 1 << ls; sub[b] = (first virtual cell of bin b) << 3 | ls, and
+    // vstart[] is the start table of the virtual cells (x fastest inside a bin)
+    int two_level;
+    uint32_t nvirt;
 };
+constexpr uint32_t kDenseBin = 32;   // a uniform (Poisson, 8 per bin) input never reaches it
+constexpr uint32_t kSubPpc = 8;      // sub-grid sized for <= kSubPpc seeds per virtual cell
+constexpr int kMaxSubLog = 5;        // s <= 32
 
 // One seed in grid order: 32 bytes, read with two 16-byte loads.
 struct __align__(16) Seed {
@@ -114,6 +122,7 @@ struct Ctx {
     DevBuf<double> wgt;        // user order
     GridDesc grid;
     DevBuf<uint32_t> cellid, rank, cell_start, perm, scan_tmp;
+    DevBuf<uint32_t> sub, vstart, vcount;   // two-level grid only
     DevBuf<Seed> sorted;
 
     // kNN table of the cell pipeline (rows in pass order, ids in grid order + n*instance)
@@ -173,7 +182,7 @@ struct CellJob {
 int run_cells(Ctx* c, const CellJob& job);
 // fused.cu
 int run_cells_fused(Ctx* c, uint32_t nq, const uint32_t* qlist, int want_faces,
-                    int collect_events, float target, int want_energy);
+                    int collect_events, float target, int want_energy, int big);
 int compact_failed(Ctx* c, const uint32_t* qlist_in, uint32_t nq_in, uint32_t* qlist_out,
                    uint32_t* rows_out, uint32_t* count_out_host, uint8_t mask);
 int lloyd_update(Ctx* c);

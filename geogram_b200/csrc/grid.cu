@@ -55,7 +55,7 @@ __global__ void bbox_kernel(const double* __restrict__ xyz, uint32_t n, double* 
 
 __global__ void bin_count_kernel(const double* __restrict__ xyz, uint32_t n, GridDesc G,
                                  uint32_t* __restrict__ cellid, uint32_t* __restrict__ rank,
-                                 uint32_t* __restrict__ counts) {
+                                 uint32_t* __restrict__ counts, uint32_t* __restrict__ dense_flag) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if(i >= n) {
         return;
@@ -65,7 +65,79 @@ __global__ void bin_count_kernel(const double* __restrict__ xyz, uint32_t n, Gri
     cell_coords(G, x, y, z, ix, iy, iz);
     uint32_t c = uint32_t(ix) + uint32_t(G.g[0]) * (uint32_t(iy) + uint32_t(G.g[1]) * uint32_t(iz));
     cellid[i] = c;
-    rank[i] = atomicAdd(&counts[c], 1u);
+    uint32_t r = atomicAdd(&counts[c], 1u);
+    rank[i] = r;
+    if(r == kDenseBin) {
+        *dense_flag = 1u;   // some bin holds more than kDenseBin seeds: two-level build
+    }
+}
+
+// ---- two-level build (clustered seeds) ----
+// sub-grid resolution of every bin and the number of virtual cells it contributes
+__global__ void sub_layout_kernel(uint32_t ncell, const uint32_t* __restrict__ counts,
+                                  uint32_t* __restrict__ nv, uint32_t* __restrict__ sub) {
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if(b >= ncell) {
+        return;
+    }
+    uint32_t cnt = counts[b];
+    uint32_t ls = 0;
+    if(cnt > kDenseBin) {
+        while(ls < uint32_t(kMaxSubLog) && (uint64_t(kSubPpc) << (3 * ls)) < cnt) {
+            ++ls;
+        }
+    }
+    nv[b] = 1u << (3 * ls);
+    sub[b] = ls;
+}
+
+__global__ void sub_pack_kernel(uint32_t ncell, const uint32_t* __restrict__ voff,
+                                uint32_t* __restrict__ sub) {
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if(b < ncell) {
+        sub[b] = (voff[b] << 3) | sub[b];
+    }
+}
+
+__global__ void vcell_count_kernel(const double* __restrict__ xyz, uint32_t n, GridDesc G,
+                                   const uint32_t* __restrict__ sub, uint32_t* __restrict__ cellid,
+                                   uint32_t* __restrict__ rank, uint32_t* __restrict__ vcounts) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) {
+        return;
+    }
+    const uint32_t b = cellid[i];
+    const uint32_t sw = sub[b];
+    const uint32_t ls = sw & 7u;
+    uint32_t v = sw >> 3;
+    if(ls) {
+        const int s = 1 << ls;
+        const int gx = G.g[0], gy = G.g[1];
+        const int ix = int(b % uint32_t(gx)), iy = int((b / uint32_t(gx)) % uint32_t(gy)),
+                  iz = int(b / (uint32_t(gx) * uint32_t(gy)));
+        const int bc[3] = {ix, iy, iz};
+        int f[3];
+        for(int a = 0; a < 3; ++a) {
+            // same expression as the walk (fused.cu): fine coordinate at level ls, clamped to the bin
+            int fa = int(floor((xyz[3 * size_t(i) + a] - G.lo[a]) * (G.inv_w[a] * double(s))));
+            f[a] = clampi(fa - bc[a] * s, 0, s - 1);
+        }
+        v += uint32_t(f[0] + s * (f[1] + s * f[2]));
+    }
+    cellid[i] = v;
+    rank[i] = atomicAdd(&vcounts[v], 1u);
+}
+
+// level-1 start table (knn.cu, cell.cu) from the virtual one
+__global__ void level1_start_kernel(uint32_t ncell, uint32_t n, const uint32_t* __restrict__ sub,
+                                    const uint32_t* __restrict__ vstart,
+                                    uint32_t* __restrict__ cell_start) {
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if(b < ncell) {
+        cell_start[b] = vstart[sub[b] >> 3];
+    } else if(b == ncell) {
+        cell_start[b] = n;
+    }
 }
 
 // ---- exclusive scan of uint32 (three phases, 4096 items per block) ----
@@ -302,24 +374,80 @@ int build_grid(Ctx* c) {
         return rc;
     }
     uint32_t ntiles = (G.ncell + kScanTile - 1) / kScanTile;
-    // counters live after the tile sums in scan_tmp
+    // counters live after the tile sums in scan_tmp; one word in front of them is the dense flag
     if((rc = c->scan_tmp.reserve(size_t(ntiles) + size_t(G.ncell) + 4096))) {
         return rc;
     }
     uint32_t* tile_sums = c->scan_tmp.p;
-    uint32_t* counts = c->scan_tmp.p + ntiles + 1;
-    B200_CUDA_CHECK(cudaMemsetAsync(counts, 0, size_t(G.ncell) * sizeof(uint32_t), st));
+    uint32_t* dense_flag = c->scan_tmp.p + ntiles + 1;
+    uint32_t* counts = c->scan_tmp.p + ntiles + 2;
+    B200_CUDA_CHECK(cudaMemsetAsync(dense_flag, 0, (size_t(G.ncell) + 1) * sizeof(uint32_t), st));
     uint32_t nblk = (n + kThreads - 1) / kThreads;
-    bin_count_kernel<<<nblk, kThreads, 0, st>>>(c->xyz.p, n, G, c->cellid.p, c->rank.p, counts);
-    scan_tile_sums<<<ntiles, kThreads, 0, st>>>(counts, G.ncell, tile_sums);
+    bin_count_kernel<<<nblk, kThreads, 0, st>>>(c->xyz.p, n, G, c->cellid.p, c->rank.p, counts, dense_flag);
+    c->stats.gpu_launches++;
+    uint32_t dense = 0;
+    B200_CUDA_CHECK(cudaMemcpyAsync(&dense, dense_flag, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    B200_CUDA_CHECK(cudaStreamSynchronize(st));
+    G.two_level = dense ? 1 : 0;
+    G.nvirt = G.ncell;
+    if(!dense) {
+        scan_tile_sums<<<ntiles, kThreads, 0, st>>>(counts, G.ncell, tile_sums);
+        scan_of_sums<<<1, kThreads, 0, st>>>(tile_sums, ntiles);
+        scan_apply<<<ntiles, kThreads, 0, st>>>(counts, G.ncell, tile_sums, c->cell_start.p, n);
+        bin_scatter_kernel<<<nblk, kThreads, 0, st>>>(c->xyz.p, c->has_w ? c->wgt.p : nullptr, n,
+                                                      c->cellid.p, c->rank.p, c->cell_start.p,
+                                                      c->sorted.p, c->perm.p);
+        sort_bins_kernel<<<(G.ncell + kThreads - 1) / kThreads, kThreads, 0, st>>>(
+            G.ncell, c->cell_start.p, c->sorted.p, c->perm.p);
+        c->stats.gpu_launches += 5;
+        B200_CUDA_CHECK(cudaGetLastError());
+        return B200VOR_OK;
+    }
+    // ---- clustered seeds: dense bins get their own sub-grid; the counting sort runs over
+    //      the virtual cells, so that the seeds of a bin stay contiguous (level-1 table valid) ----
+    if((rc = c->sub.reserve(size_t(G.ncell) + 1)) || (rc = c->vcount.reserve(size_t(G.ncell) + 1))) {
+        return rc;
+    }
+    uint32_t cblk = (G.ncell + kThreads - 1) / kThreads;
+    uint32_t* nv = c->vcount.p;         // per-bin virtual-cell counts, then re-used below
+    sub_layout_kernel<<<cblk, kThreads, 0, st>>>(G.ncell, counts, nv, c->sub.p);
+    // voff = exclusive scan of nv (written over `counts`, no longer needed)
+    scan_tile_sums<<<ntiles, kThreads, 0, st>>>(nv, G.ncell, tile_sums);
     scan_of_sums<<<1, kThreads, 0, st>>>(tile_sums, ntiles);
-    scan_apply<<<ntiles, kThreads, 0, st>>>(counts, G.ncell, tile_sums, c->cell_start.p, n);
+    scan_apply<<<ntiles, kThreads, 0, st>>>(nv, G.ncell, tile_sums, counts, 0u);
+    sub_pack_kernel<<<cblk, kThreads, 0, st>>>(G.ncell, counts, c->sub.p);
+    c->stats.gpu_launches += 5;
+    // total number of virtual cells = voff[last] + nv[last]
+    uint32_t last[2];
+    B200_CUDA_CHECK(cudaMemcpyAsync(&last[0], counts + (G.ncell - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    B200_CUDA_CHECK(cudaMemcpyAsync(&last[1], nv + (G.ncell - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    B200_CUDA_CHECK(cudaStreamSynchronize(st));
+    const uint64_t nvirt64 = uint64_t(last[0]) + last[1];
+    if(nvirt64 >= (1ull << 29)) {
+        set_error("build_grid: %llu virtual cells exceed the two-level table", (unsigned long long)nvirt64);
+        return B200VOR_ERR_CAPACITY;
+    }
+    G.nvirt = uint32_t(nvirt64);
+    uint32_t vtiles = (G.nvirt + kScanTile - 1) / kScanTile;
+    if((rc = c->vstart.reserve(size_t(G.nvirt) + 1)) ||
+       (rc = c->vcount.reserve(size_t(G.nvirt) + size_t(vtiles) + 64))) {
+        return rc;
+    }
+    uint32_t* vcounts = c->vcount.p;
+    uint32_t* vtile_sums = c->vcount.p + G.nvirt + 1;
+    B200_CUDA_CHECK(cudaMemsetAsync(vcounts, 0, size_t(G.nvirt) * sizeof(uint32_t), st));
+    vcell_count_kernel<<<nblk, kThreads, 0, st>>>(c->xyz.p, n, G, c->sub.p, c->cellid.p, c->rank.p, vcounts);
+    scan_tile_sums<<<vtiles, kThreads, 0, st>>>(vcounts, G.nvirt, vtile_sums);
+    scan_of_sums<<<1, kThreads, 0, st>>>(vtile_sums, vtiles);
+    scan_apply<<<vtiles, kThreads, 0, st>>>(vcounts, G.nvirt, vtile_sums, c->vstart.p, n);
     bin_scatter_kernel<<<nblk, kThreads, 0, st>>>(c->xyz.p, c->has_w ? c->wgt.p : nullptr, n,
-                                                  c->cellid.p, c->rank.p, c->cell_start.p,
+                                                  c->cellid.p, c->rank.p, c->vstart.p,
                                                   c->sorted.p, c->perm.p);
-    sort_bins_kernel<<<(G.ncell + kThreads - 1) / kThreads, kThreads, 0, st>>>(
-        G.ncell, c->cell_start.p, c->sorted.p, c->perm.p);
-    c->stats.gpu_launches += 6;
+    sort_bins_kernel<<<(G.nvirt + kThreads - 1) / kThreads, kThreads, 0, st>>>(
+        G.nvirt, c->vstart.p, c->sorted.p, c->perm.p);
+    level1_start_kernel<<<(G.ncell + 1 + kThreads - 1) / kThreads, kThreads, 0, st>>>(
+        G.ncell, n, c->sub.p, c->vstart.p, c->cell_start.p);
+    c->stats.gpu_launches += 7;
     B200_CUDA_CHECK(cudaGetLastError());
     return B200VOR_OK;
 }
