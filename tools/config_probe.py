@@ -53,10 +53,11 @@ def main():
                    k_pass=s["k_pass"][: s["passes"]])
     else:
         kmax = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+        mode = int(sys.argv[4]) if len(sys.argv) > 4 else 0
         xyz = oracles.clustered_seeds(n, 12345)
         t0 = time.perf_counter()
         ctx.set_points(xyz)
-        ctx.compute_cells(kmax=kmax)
+        ctx.compute_cells(kmax=kmax, mode=mode)
         res["wall_s_set_points_plus_cells"] = time.perf_counter() - t0
         m, mg, st = ctx.get_cells()
         s = ctx.stats()

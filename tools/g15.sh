@@ -1,0 +1,2 @@
+#!/bin/bash
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "clustered" 2>&1 | tail -15
