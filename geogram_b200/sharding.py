@@ -19,6 +19,15 @@ def shard_sizes(n_total, world):
     return [shard_range(n_total, r, world)[1] - shard_range(n_total, r, world)[0] for r in range(world)]
 
 
+def slab_order(full):
+    """Permutation that sorts the seeds by x: with `shard_range`, rank r then owns the r-th
+    x-quantile SLAB of the domain (equal seed counts, cuts at the quantiles -- SURVEY 8(e)), so the
+    cells a rank computes are spatially coherent and share their neighbourhoods in L1/L2.
+    Deterministic (stable sort), hence identical on every rank."""
+    import torch
+    return torch.argsort(full[:, 0], stable=True)
+
+
 def allgather_rows(dist, full, mine):
     """full[n_total, c] <- concatenation over ranks of mine[(last-first), c].
 
@@ -80,9 +89,16 @@ class ShardedLloyd(object):
         self._comm = []
 
     # ---- seeds in ----
-    def set_seeds_device(self, full):
-        """full: (n_total,3) float64 device tensor holding ALL seeds (identical on every rank)."""
-        self.full.copy_(full)
+    def set_seeds_device(self, full, slabs=False):
+        """full: (n_total,3) float64 device tensor holding ALL seeds (identical on every rank).
+        slabs=True first re-orders the rows into x-quantile slabs (`slab_order`); the permutation
+        is kept in `self.order` (row k of the job is row order[k] of the caller)."""
+        self.order = None
+        if slabs:
+            self.order = slab_order(full)
+            self.full.copy_(full[self.order])
+        else:
+            self.full.copy_(full)
         self.ctx.set_points_device(self.n_total, self.full.data_ptr())
         self._take("ms_grid")
 

@@ -54,6 +54,22 @@ def test_shard_ranges_partition():
         assert max(shard_sizes(n, w)) - min(shard_sizes(n, w)) <= 1
 
 
+def test_slab_order_gives_spatial_slabs():
+    """slab_order + shard_range: rank r owns the r-th x-quantile slab, equal counts"""
+    import torch
+    from geogram_b200.sharding import slab_order
+    g = torch.Generator().manual_seed(5)
+    full = torch.rand((1001, 3), dtype=torch.float64, generator=g)
+    order = slab_order(full)
+    assert sorted(order.tolist()) == list(range(1001))
+    x = full[order][:, 0]
+    prev_max = -1.0
+    for r in range(4):
+        a, b = shard_range(1001, r, 4)
+        assert x[a:b].min().item() >= prev_max
+        prev_max = x[a:b].max().item()
+
+
 @pytest.mark.parametrize("world,n_total", [(2, 1000), (3, 1001)])
 def test_allgather_rows_gloo(world, n_total):
     ctx = mp.get_context("spawn")
