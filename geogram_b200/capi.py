@@ -27,7 +27,7 @@ EXPORTS = [
     "b200vor_version", "b200vor_last_error", "b200vor_create", "b200vor_destroy",
     "b200vor_set_domain_box", "b200vor_set_domain_periodic", "b200vor_set_points",
     "b200vor_knn", "b200vor_knn_points", "b200vor_compute_cells", "b200vor_get_cells",
-    "b200vor_get_faces", "b200vor_get_cvt", "b200vor_lloyd", "b200vor_get_stats",
+    "b200vor_get_faces", "b200vor_get_cvt", "b200vor_otm_newton", "b200vor_lloyd", "b200vor_get_stats",
     "b200vor_set_points_per_cell", "b200vor_set_stream", "b200vor_set_query_range",
 ]
 
@@ -36,6 +36,23 @@ class CellParams(ctypes.Structure):
     _fields_ = [("k0", ctypes.c_uint32), ("kmax", ctypes.c_uint32),
                 ("want_faces", ctypes.c_uint32), ("mode", ctypes.c_uint32),
                 ("want_energy", ctypes.c_uint32)]
+
+
+class OtmParams(ctypes.Structure):
+    _fields_ = [("max_newton", ctypes.c_uint32), ("max_cg", ctypes.c_uint32),
+                ("cg_tol", ctypes.c_double), ("epsilon", ctypes.c_double),
+                ("total_mass", ctypes.c_double)]
+
+
+class OtmResult(ctypes.Structure):
+    _fields_ = [("newton_iters", ctypes.c_uint32), ("cg_iters", ctypes.c_uint32),
+                ("cell_evals", ctypes.c_uint32), ("converged", ctypes.c_int32),
+                ("initial_error", ctypes.c_double), ("final_error", ctypes.c_double),
+                ("max_rel_error", ctypes.c_double), ("min_volume", ctypes.c_double),
+                ("sum_volume", ctypes.c_double), ("last_alpha", ctypes.c_double)]
+
+    def as_dict(self):
+        return {name: getattr(self, name) for name, _ in self._fields_}
 
 
 class Stats(ctypes.Structure):
@@ -95,6 +112,7 @@ def load_library():
     lib.b200vor_get_cells.argtypes = [vp, vp, vp, vp, i32]
     lib.b200vor_get_faces.argtypes = [vp, vp, vp, vp, u32, i32]
     lib.b200vor_get_cvt.argtypes = [vp, vp, vp, ctypes.POINTER(dbl), i32]
+    lib.b200vor_otm_newton.argtypes = [vp, vp, vp, ctypes.POINTER(OtmParams), ctypes.POINTER(OtmResult), i32]
     lib.b200vor_lloyd.argtypes = [vp, u32, ctypes.POINTER(CellParams), vp, i32]
     lib.b200vor_get_stats.argtypes = [vp, ctypes.POINTER(Stats)]
     lib.b200vor_set_points_per_cell.argtypes = [vp, dbl]
@@ -221,6 +239,17 @@ class Context(object):
         tot = ctypes.c_double(0.0)
         self._check(self.lib.b200vor_get_cvt(self.h, _ptr(f), _ptr(g), ctypes.byref(tot), 0))
         return tot.value, f, g
+
+    def otm_newton(self, nu=None, w0=None, max_newton=0, max_cg=0, cg_tol=0.0, epsilon=0.0, total_mass=0.0):
+        """Semi-discrete optimal transport (damped Newton on the Laguerre weights) for the points
+        of set_points: returns (w, result dict).  nu: target measures or None (uniform)."""
+        w = np.zeros(self.n) if w0 is None else np.array(w0, np.float64, copy=True)
+        if nu is not None:
+            nu = np.ascontiguousarray(nu, np.float64)
+        p = OtmParams(int(max_newton), int(max_cg), float(cg_tol), float(epsilon), float(total_mass))
+        r = OtmResult()
+        self._check(self.lib.b200vor_otm_newton(self.h, _ptr(nu), _ptr(w), ctypes.byref(p), ctypes.byref(r), 0))
+        return w, r.as_dict()
 
     def lloyd(self, iters, k0=0, kmax=0, mode=0, want_xyz=True, out=None):
         """out: optional preallocated (n,3) float64 host array (e.g. pinned) for the result"""

@@ -301,6 +301,19 @@ int cells_pipeline(Ctx* c, const b200vor_cell_params* params, bool collect_event
     return B200VOR_OK;
 }
 
+}  // namespace
+
+// cell pass with face lists on the context's current weights (otm.cu)
+int otm_cells(Ctx* c) {
+    b200vor_cell_params p = {0, 0, 1, 0, 0};
+    int rc = cells_pipeline(c, &p, false);
+    return rc;
+}
+int otm_newton(Ctx* c, const double* nu, double* w, const b200vor_otm_params* prm, b200vor_otm_result* res,
+               int on_device);
+
+namespace {
+
 int ensure_grid(Ctx* c) {
     Timer T(c->stream);
     T.mark(1);
@@ -681,6 +694,24 @@ int b200vor_get_cvt(b200vor_ctx* h, double* f_cell, double* g, double* f_total, 
     }
     B200_CUDA_CHECK(cudaStreamSynchronize(c->stream));
     return B200VOR_OK;
+}
+
+int b200vor_otm_newton(b200vor_ctx* h, const double* nu, double* w, const b200vor_otm_params* params,
+                       b200vor_otm_result* result, int on_device) {
+    if(!h || !w || h->c.n == 0) {
+        set_error("b200vor_otm_newton: needs a context with points and a weight array");
+        return B200VOR_ERR_ARG;
+    }
+    Ctx* c = &h->c;
+    if(c->q0 > 0 || c->q1 < c->n) {
+        set_error("b200vor_otm_newton: not available on a sharded context (b200vor_set_query_range)");
+        return B200VOR_ERR_ARG;
+    }
+    B200_CUDA_CHECK(cudaSetDevice(c->device));
+    c->stats.ms_grid = c->stats.ms_knn = c->stats.ms_clip = 0.f;
+    int rc = otm_newton(c, nu, w, params, result, on_device);
+    c->stats.ms_total = c->stats.ms_grid + c->stats.ms_knn + c->stats.ms_clip;
+    return rc;
 }
 
 int b200vor_get_faces(b200vor_ctx* h, uint32_t* nfaces, uint32_t* face_nbr, double* face_area,

@@ -1,0 +1,535 @@
+// otm.cu -- semi-discrete optimal transport on the device: damped Newton on the Laguerre weights.
+//
+// SURVEY.md 8(f) rank 1 / 8(a) a20.  The reference's solver lives in BrunoLevy/exploragram
+// (OptimalTransportMap3d; NOT under /root/reference, unpinned -- call sites
+// src/examples/exploragram/compute_OTM/main.cpp:284-297), so this file restates the PUBLISHED
+// algorithm and is parity-unpinned against exploragram itself:
+//   * B. Levy, "A numerical algorithm for L2 semi-discrete optimal transport in 3D" (M2AN 2015):
+//     objective, gradient g_i = vol(Lag_i) - nu_i, Hessian H_ij = A_ij / (2 |p_i - p_j|);
+//   * Kitagawa, Merigot, Thibert, "Convergence of a Newton algorithm for semi-discrete optimal
+//     transport" (JEMS 2019), Algorithm 1: damped Newton, step halved until every cell keeps at
+//     least eps0 = 1/2 min(min_i vol_i(w0), min_i nu_i) and the error decreases by (1 - alpha/2).
+// What IS pinned against the reference are the inputs of every Newton step: Laguerre cell
+// volumes and facet areas A_ij (tests/test_gpu_parity.py against the exact Delaunay oracle).
+//
+// All vectors stay in HBM.  Per Newton iteration: one cell pass with face lists (fused.cu), one
+// coefficient kernel, a Jacobi-preconditioned CG whose SpMV reads the face lists as an ELL
+// matrix (16 lanes per row, coalesced 64-byte segments), and one cell pass per damping trial.
+// Every reduction is a fixed-partition block tree + ordered host sum: bitwise reproducible.
+#include "common.cuh"
+
+#include <math.h>
+#include <string.h>
+
+#include <vector>
+
+namespace b200vor {
+
+int build_grid(Ctx* c);
+int otm_cells(Ctx* c);   // capi.cu: cell pass with face lists on the current weights
+
+namespace {
+
+constexpr int kNB = 256;       // reduction blocks
+constexpr int kNT = 256;       // threads per block
+constexpr uint32_t kFcap = 64;
+
+// translation (in periods) of periodic instance `inst`: inverse of translation_to_instance
+__device__ inline void instance_translation(uint32_t inst, int& tx, int& ty, int& tz) {
+    // reorder_instances: 0 -> 13, 1..13 -> 0..12, 14..26 unchanged (periodic.cpp:80-84)
+    int i = inst == 0 ? 13 : (inst <= 13 ? int(inst) - 1 : int(inst));
+    tz = i % 3 - 1;
+    ty = (i / 3) % 3 - 1;
+    tx = i / 9 - 1;
+}
+
+// c_if = A_if / (2 |p_i - p_j|) for every face f of every cell i, column j_f = real index of the
+// neighbour (box faces: coefficient 0); diag_i = sum_f c_if.  16 lanes per row.
+__global__ void otm_coef_kernel(uint32_t n, const double* __restrict__ xyz, int periodic, double period,
+                                const uint32_t* __restrict__ nfaces, const uint32_t* __restrict__ face_nbr,
+                                const double* __restrict__ face_area, uint32_t* __restrict__ col,
+                                double* __restrict__ coef, double* __restrict__ diag) {
+    const uint32_t lane = threadIdx.x & 15u;
+    const uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    const bool alive = row < n;
+    const uint32_t r = alive ? row : 0u;
+    const uint32_t nf = alive ? min(nfaces[r], kFcap) : 0u;
+    const double px = xyz[3 * size_t(r)], py = xyz[3 * size_t(r) + 1], pz = xyz[3 * size_t(r) + 2];
+    double d = 0.0;
+    for(uint32_t f = lane; f < kFcap; f += 16u) {
+        uint32_t j = 0;
+        double cf = 0.0;
+        if(f < nf) {
+            const uint32_t id = face_nbr[size_t(r) * kFcap + f];
+            if(id < B200VOR_BOX_ID) {
+                j = id % n;
+                const uint32_t inst = id / n;
+                int tx = 0, ty = 0, tz = 0;
+                if(periodic) {
+                    instance_translation(inst, tx, ty, tz);
+                }
+                const double qx = xyz[3 * size_t(j)] + tx * period - px;
+                const double qy = xyz[3 * size_t(j) + 1] + ty * period - py;
+                const double qz = xyz[3 * size_t(j) + 2] + tz * period - pz;
+                const double dist = sqrt(qx * qx + qy * qy + qz * qz);
+                cf = dist > 0.0 ? face_area[size_t(r) * kFcap + f] / (2.0 * dist) : 0.0;
+            } else {
+                j = r;
+            }
+        } else {
+            j = r;
+        }
+        if(alive) {
+            col[size_t(r) * kFcap + f] = j;
+            coef[size_t(r) * kFcap + f] = cf;
+        }
+        d += cf;
+    }
+    for(int o = 8; o > 0; o >>= 1) {
+        d += __shfl_xor_sync(0xffffffffu, d, o, 16);
+    }
+    if(alive && lane == 0) {
+        diag[r] = d;
+    }
+}
+
+// y = L x, L_ii = sum_f c_if, L_ij = -c_if: y_i = sum_f c_if (x_i - x_jf).  16 lanes per row.
+__global__ void otm_spmv_kernel(uint32_t n, const uint32_t* __restrict__ nfaces, const uint32_t* __restrict__ col,
+                                const double* __restrict__ coef, const double* __restrict__ x,
+                                double* __restrict__ y) {
+    const uint32_t lane = threadIdx.x & 15u;
+    const uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    const bool alive = row < n;
+    const uint32_t r = alive ? row : 0u;
+    const uint32_t nf = alive ? min(nfaces[r], kFcap) : 0u;
+    const double xi = x[r];
+    double acc = 0.0;
+    for(uint32_t f = lane; f < nf; f += 16u) {
+        acc += coef[size_t(r) * kFcap + f] * (xi - x[col[size_t(r) * kFcap + f]]);
+    }
+    for(int o = 8; o > 0; o >>= 1) {
+        acc += __shfl_xor_sync(0xffffffffu, acc, o, 16);
+    }
+    if(alive && lane == 0) {
+        y[r] = acc;
+    }
+}
+
+// fixed-partition block reductions: block b owns the contiguous slice [b*per, (b+1)*per)
+__device__ inline double block_sum(double v) {
+    __shared__ double sm[kNT];
+    sm[threadIdx.x] = v;
+    __syncthreads();
+    for(uint32_t o = kNT / 2; o > 0; o >>= 1) {
+        if(threadIdx.x < o) {
+            sm[threadIdx.x] += sm[threadIdx.x + o];
+        }
+        __syncthreads();
+    }
+    double r = sm[0];
+    __syncthreads();
+    return r;
+}
+
+__global__ void dot_kernel(uint32_t n, const double* __restrict__ a, const double* __restrict__ b,
+                           double* __restrict__ part) {
+    const uint32_t per = (n + gridDim.x - 1) / gridDim.x;
+    const uint32_t lo = blockIdx.x * per, hi = min(n, lo + per);
+    double acc = 0.0;
+    for(uint32_t i = lo + threadIdx.x; i < hi; i += kNT) {
+        acc += a[i] * b[i];
+    }
+    acc = block_sum(acc);
+    if(threadIdx.x == 0) {
+        part[blockIdx.x] = acc;
+    }
+}
+
+// x += alpha p ; r -= alpha q ; z = r / diag ; partials of r.z and r.r
+__global__ void cg_update_kernel(uint32_t n, double alpha, const double* __restrict__ p, const double* __restrict__ q,
+                                 const double* __restrict__ diag, double* __restrict__ x, double* __restrict__ r,
+                                 double* __restrict__ z, double* __restrict__ part) {
+    const uint32_t per = (n + gridDim.x - 1) / gridDim.x;
+    const uint32_t lo = blockIdx.x * per, hi = min(n, lo + per);
+    double rz = 0.0, rr = 0.0;
+    for(uint32_t i = lo + threadIdx.x; i < hi; i += kNT) {
+        x[i] += alpha * p[i];
+        const double ri = r[i] - alpha * q[i];
+        r[i] = ri;
+        const double di = diag[i];
+        const double zi = di > 0.0 ? ri / di : 0.0;
+        z[i] = zi;
+        rz += ri * zi;
+        rr += ri * ri;
+    }
+    rz = block_sum(rz);
+    rr = block_sum(rr);
+    if(threadIdx.x == 0) {
+        part[blockIdx.x] = rz;
+        part[gridDim.x + blockIdx.x] = rr;
+    }
+}
+
+// p = z + beta p
+__global__ void cg_dir_kernel(uint32_t n, double beta, const double* __restrict__ z, double* __restrict__ p) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i < n) {
+        p[i] = z[i] + beta * p[i];
+    }
+}
+
+// b = nu - vol (nu == NULL: uniform total / n) ; partials: sum (vol-nu)^2, max |vol-nu|/nu, min vol, sum vol
+__global__ void otm_residual_kernel(uint32_t n, const double* __restrict__ vol, const double* __restrict__ nu,
+                                    double nu_uniform, double* __restrict__ b, double* __restrict__ part) {
+    __shared__ double smx[kNT], smn[kNT];
+    const uint32_t per = (n + gridDim.x - 1) / gridDim.x;
+    const uint32_t lo = blockIdx.x * per, hi = min(n, lo + per);
+    double s2 = 0.0, sv = 0.0, mx = 0.0, mn = 1e300;
+    for(uint32_t i = lo + threadIdx.x; i < hi; i += kNT) {
+        const double v = vol[i], t = nu ? nu[i] : nu_uniform;
+        const double g = t - v;
+        if(b) {
+            b[i] = g;
+        }
+        s2 += g * g;
+        sv += v;
+        mx = fmax(mx, fabs(g) / t);
+        mn = fmin(mn, v);
+    }
+    s2 = block_sum(s2);
+    sv = block_sum(sv);
+    smx[threadIdx.x] = mx;
+    smn[threadIdx.x] = mn;
+    __syncthreads();
+    for(uint32_t o = kNT / 2; o > 0; o >>= 1) {
+        if(threadIdx.x < o) {
+            smx[threadIdx.x] = fmax(smx[threadIdx.x], smx[threadIdx.x + o]);
+            smn[threadIdx.x] = fmin(smn[threadIdx.x], smn[threadIdx.x + o]);
+        }
+        __syncthreads();
+    }
+    if(threadIdx.x == 0) {
+        part[blockIdx.x] = s2;
+        part[gridDim.x + blockIdx.x] = sv;
+        part[2 * gridDim.x + blockIdx.x] = smx[0];
+        part[3 * gridDim.x + blockIdx.x] = smn[0];
+    }
+}
+
+// out = a + s * d ; z0 = r / diag (s == 0 form used to initialise CG)
+__global__ void axpy_out_kernel(uint32_t n, const double* __restrict__ a, double s, const double* __restrict__ d,
+                                double* __restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i < n) {
+        out[i] = a[i] + s * d[i];
+    }
+}
+
+__global__ void jacobi_kernel(uint32_t n, const double* __restrict__ r, const double* __restrict__ diag,
+                              double* __restrict__ z, double* __restrict__ p) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i < n) {
+        const double di = diag[i];
+        const double zi = di > 0.0 ? r[i] / di : 0.0;
+        z[i] = zi;
+        p[i] = zi;
+    }
+}
+
+struct Resid {
+    double norm2, sumvol, maxrel, minvol;
+};
+
+struct Work {
+    DevBuf<double> nu, b, x, r, z, p, q, diag, coef, w0, w1, part;
+    DevBuf<uint32_t> col;
+    ~Work() { release(); }
+    void release() {
+        nu.release(); b.release(); x.release(); r.release(); z.release(); p.release(); q.release();
+        diag.release(); coef.release(); w0.release(); w1.release(); part.release(); col.release();
+    }
+};
+
+int host_sum(Ctx* c, const double* part, int count, double* out) {
+    std::vector<double> h(count);
+    B200_CUDA_CHECK(cudaMemcpyAsync(h.data(), part, sizeof(double) * count, cudaMemcpyDeviceToHost, c->stream));
+    B200_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    memcpy(out, h.data(), sizeof(double) * count);
+    return B200VOR_OK;
+}
+
+int residual(Ctx* c, Work& W, const double* nu, double nu_uniform, double* b, Resid* R) {
+    otm_residual_kernel<<<kNB, kNT, 0, c->stream>>>(c->n, c->m.p, nu, nu_uniform, b, W.part.p);
+    c->stats.gpu_launches++;
+    double h[4 * kNB];
+    int rc = host_sum(c, W.part.p, 4 * kNB, h);
+    if(rc) {
+        return rc;
+    }
+    R->norm2 = 0.0; R->sumvol = 0.0; R->maxrel = 0.0; R->minvol = 1e300;
+    for(int k = 0; k < kNB; ++k) {
+        R->norm2 += h[k];
+        R->sumvol += h[kNB + k];
+        R->maxrel = fmax(R->maxrel, h[2 * kNB + k]);
+        R->minvol = fmin(R->minvol, h[3 * kNB + k]);
+    }
+    R->norm2 = sqrt(R->norm2);
+    return B200VOR_OK;
+}
+
+int dot(Ctx* c, Work& W, const double* a, const double* b, double* out) {
+    dot_kernel<<<kNB, kNT, 0, c->stream>>>(c->n, a, b, W.part.p);
+    c->stats.gpu_launches++;
+    double h[kNB];
+    int rc = host_sum(c, W.part.p, kNB, h);
+    if(rc) {
+        return rc;
+    }
+    double s = 0.0;
+    for(int k = 0; k < kNB; ++k) {
+        s += h[k];
+    }
+    *out = s;
+    return B200VOR_OK;
+}
+
+// weights -> context, grid rebuilt (the weight travels with the seed in `sorted`), cells + faces
+int eval_cells(Ctx* c, const double* w_dev, double wmax) {
+    int rc;
+    if((rc = c->wgt.reserve(c->n))) {
+        return rc;
+    }
+    B200_CUDA_CHECK(cudaMemcpyAsync(c->wgt.p, w_dev, size_t(c->n) * sizeof(double), cudaMemcpyDeviceToDevice,
+                                    c->stream));
+    c->has_w = true;
+    c->wmax = wmax;
+    if((rc = build_grid(c))) {
+        return rc;
+    }
+    c->grid_dirty = false;
+    return otm_cells(c);
+}
+
+__global__ void max_part_kernel(uint32_t n, const double* __restrict__ w, double* __restrict__ part) {
+    __shared__ double sm[kNT];
+    const uint32_t per = (n + gridDim.x - 1) / gridDim.x;
+    const uint32_t lo = blockIdx.x * per, hi = min(n, lo + per);
+    double mx = -1e300;
+    for(uint32_t i = lo + threadIdx.x; i < hi; i += kNT) {
+        mx = fmax(mx, w[i]);
+    }
+    sm[threadIdx.x] = mx;
+    __syncthreads();
+    for(uint32_t o = kNT / 2; o > 0; o >>= 1) {
+        if(threadIdx.x < o) {
+            sm[threadIdx.x] = fmax(sm[threadIdx.x], sm[threadIdx.x + o]);
+        }
+        __syncthreads();
+    }
+    if(threadIdx.x == 0) {
+        part[blockIdx.x] = sm[0];
+    }
+}
+
+int vec_max(Ctx* c, Work& W, const double* w, double* out) {
+    max_part_kernel<<<kNB, kNT, 0, c->stream>>>(c->n, w, W.part.p);
+    c->stats.gpu_launches++;
+    double h[kNB];
+    int rc = host_sum(c, W.part.p, kNB, h);
+    if(rc) {
+        return rc;
+    }
+    double m = h[0];
+    for(int k = 1; k < kNB; ++k) {
+        m = fmax(m, h[k]);
+    }
+    *out = m;
+    return B200VOR_OK;
+}
+
+}  // namespace
+
+int otm_newton(Ctx* c, const double* nu_in, double* w_io, const b200vor_otm_params* prm, b200vor_otm_result* res,
+               int on_device) {
+    b200vor_otm_params P = {50, 1000, 1e-8, 0.01, 0.0};
+    if(prm) {
+        P = *prm;
+        if(P.max_newton == 0) P.max_newton = 50;
+        if(P.max_cg == 0) P.max_cg = 1000;
+        if(!(P.cg_tol > 0.0)) P.cg_tol = 1e-8;
+        if(!(P.epsilon > 0.0)) P.epsilon = 0.01;
+        if(!(P.total_mass > 0.0)) P.total_mass = 0.0;
+    }
+    const uint32_t n = c->n;
+    const uint32_t nblk = (n + kNT - 1) / kNT;
+    const uint32_t rblk = uint32_t((size_t(n) * 16 + kNT - 1) / kNT);
+    Work W;
+    int rc = 0;
+    b200vor_otm_result R;
+    memset(&R, 0, sizeof(R));
+    auto fail = [&](int code) { return code; };   // W releases its buffers when it goes out of scope
+    if((rc = W.b.reserve(n)) || (rc = W.x.reserve(n)) || (rc = W.r.reserve(n)) || (rc = W.z.reserve(n)) ||
+       (rc = W.p.reserve(n)) || (rc = W.q.reserve(n)) || (rc = W.diag.reserve(n)) || (rc = W.w0.reserve(n)) ||
+       (rc = W.w1.reserve(n)) || (rc = W.part.reserve(4 * kNB)) || (rc = W.coef.reserve(size_t(n) * kFcap)) ||
+       (rc = W.col.reserve(size_t(n) * kFcap))) {
+        return fail(rc);
+    }
+    cudaStream_t st = c->stream;
+    const double* nu = nullptr;
+    if(nu_in) {
+        if(on_device) {
+            nu = nu_in;
+        } else {
+            if((rc = W.nu.reserve(n))) {
+                return fail(rc);
+            }
+            if(cudaMemcpyAsync(W.nu.p, nu_in, size_t(n) * sizeof(double), cudaMemcpyHostToDevice, st) != cudaSuccess) {
+                set_error("b200vor_otm_newton: copy of nu failed");
+                return fail(B200VOR_ERR_CUDA);
+            }
+            nu = W.nu.p;
+        }
+    }
+    if(cudaMemcpyAsync(W.w0.p, w_io, size_t(n) * sizeof(double),
+                       on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st) != cudaSuccess) {
+        set_error("b200vor_otm_newton: copy of the weights failed");
+        return fail(B200VOR_ERR_CUDA);
+    }
+    // measure of the domain (uniform target = |domain| / n)
+    double domain = c->periodic ? c->period * c->period * c->period
+                                : (c->box[3] - c->box[0]) * (c->box[4] - c->box[1]) * (c->box[5] - c->box[2]);
+    const double nu_uniform = (P.total_mass > 0.0 ? P.total_mass : domain) / double(n);
+    double wmax = 0.0;
+    if((rc = vec_max(c, W, W.w0.p, &wmax)) || (rc = eval_cells(c, W.w0.p, wmax))) {
+        return fail(rc);
+    }
+    R.cell_evals = 1;
+    Resid cur;
+    if((rc = residual(c, W, nu, nu_uniform, W.b.p, &cur))) {
+        return fail(rc);
+    }
+    // smallest target measure
+    double numin = nu_uniform;
+    if(nu) {
+        // min nu = -max(-nu): reuse the residual kernel with vol := nu (min of "vol")
+        otm_residual_kernel<<<kNB, kNT, 0, st>>>(n, nu, nullptr, 1.0, nullptr, W.part.p);
+        c->stats.gpu_launches++;
+        double h[4 * kNB];
+        if((rc = host_sum(c, W.part.p, 4 * kNB, h))) {
+            return fail(rc);
+        }
+        numin = 1e300;
+        for(int k = 0; k < kNB; ++k) {
+            numin = fmin(numin, h[3 * kNB + k]);
+        }
+    }
+    // KMT: every cell keeps at least eps0
+    const double eps0 = 0.5 * fmin(cur.minvol, numin);
+    R.initial_error = cur.norm2;
+    if(!(eps0 > 0.0)) {
+        set_error("b200vor_otm_newton: an initial cell is empty (min volume %g): the damped Newton method needs "
+                  "weights whose Laguerre cells are all non-empty (KMT 2019, hypothesis of Algorithm 1)",
+                  cur.minvol);
+        return fail(B200VOR_ERR_ARG);
+    }
+    uint32_t it = 0;
+    for(; it < P.max_newton && cur.maxrel > P.epsilon; ++it) {
+        // ---- Hessian of this iterate from the face lists ----
+        otm_coef_kernel<<<rblk, kNT, 0, st>>>(n, c->xyz.p, c->periodic, c->period, c->nfaces.p, c->face_nbr.p,
+                                              c->face_area.p, W.col.p, W.coef.p, W.diag.p);
+        c->stats.gpu_launches++;
+        // ---- L delta = nu - vol by Jacobi-preconditioned CG, delta_0 = 0 ----
+        B200_CUDA_CHECK(cudaMemsetAsync(W.x.p, 0, size_t(n) * sizeof(double), st));
+        B200_CUDA_CHECK(cudaMemcpyAsync(W.r.p, W.b.p, size_t(n) * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        jacobi_kernel<<<nblk, kNT, 0, st>>>(n, W.r.p, W.diag.p, W.z.p, W.p.p);
+        c->stats.gpu_launches++;
+        double rz = 0.0, bb = 0.0;
+        if((rc = dot(c, W, W.r.p, W.z.p, &rz)) || (rc = dot(c, W, W.r.p, W.r.p, &bb))) {
+            return fail(rc);
+        }
+        const double stop2 = P.cg_tol * P.cg_tol * bb;
+        double rr = bb;
+        uint32_t k = 0;
+        for(; k < P.max_cg && rr > stop2; ++k) {
+            otm_spmv_kernel<<<rblk, kNT, 0, st>>>(n, c->nfaces.p, W.col.p, W.coef.p, W.p.p, W.q.p);
+            c->stats.gpu_launches++;
+            double pq = 0.0;
+            if((rc = dot(c, W, W.p.p, W.q.p, &pq))) {
+                return fail(rc);
+            }
+            if(!(pq > 0.0)) {
+                break;   // direction in the null space (constants): the system is solved
+            }
+            const double alpha = rz / pq;
+            cg_update_kernel<<<kNB, kNT, 0, st>>>(n, alpha, W.p.p, W.q.p, W.diag.p, W.x.p, W.r.p, W.z.p, W.part.p);
+            c->stats.gpu_launches++;
+            double h[2 * kNB];
+            if((rc = host_sum(c, W.part.p, 2 * kNB, h))) {
+                return fail(rc);
+            }
+            double rz_new = 0.0;
+            rr = 0.0;
+            for(int b = 0; b < kNB; ++b) {
+                rz_new += h[b];
+                rr += h[kNB + b];
+            }
+            const double beta = rz_new / rz;
+            rz = rz_new;
+            cg_dir_kernel<<<nblk, kNT, 0, st>>>(n, beta, W.z.p, W.p.p);
+            c->stats.gpu_launches++;
+        }
+        R.cg_iters += k;
+        // ---- KMT damping ----
+        double alpha = 1.0;
+        Resid trial = cur;
+        bool accepted = false;
+        for(int halv = 0; halv < 40; ++halv) {
+            axpy_out_kernel<<<nblk, kNT, 0, st>>>(n, W.w0.p, alpha, W.x.p, W.w1.p);
+            c->stats.gpu_launches++;
+            if((rc = vec_max(c, W, W.w1.p, &wmax)) || (rc = eval_cells(c, W.w1.p, wmax))) {
+                return fail(rc);
+            }
+            R.cell_evals++;
+            if((rc = residual(c, W, nu, nu_uniform, W.q.p, &trial))) {
+                return fail(rc);
+            }
+            if(trial.minvol >= eps0 && trial.norm2 <= (1.0 - 0.5 * alpha) * cur.norm2) {
+                accepted = true;
+                break;
+            }
+            alpha *= 0.5;
+        }
+        if(!accepted) {
+            // no admissible step: restore the cells of the last accepted weights and stop
+            if((rc = vec_max(c, W, W.w0.p, &wmax)) || (rc = eval_cells(c, W.w0.p, wmax))) {
+                return fail(rc);
+            }
+            R.cell_evals++;
+            break;
+        }
+        std::swap(W.w0.p, W.w1.p);
+        std::swap(W.w0.cap, W.w1.cap);
+        std::swap(W.b.p, W.q.p);
+        std::swap(W.b.cap, W.q.cap);
+        cur = trial;
+        R.last_alpha = alpha;
+    }
+    R.newton_iters = it;
+    R.final_error = cur.norm2;
+    R.max_rel_error = cur.maxrel;
+    R.min_volume = cur.minvol;
+    R.sum_volume = cur.sumvol;
+    R.converged = cur.maxrel <= P.epsilon ? 1 : 0;
+    if(cudaMemcpyAsync(w_io, W.w0.p, size_t(n) * sizeof(double),
+                       on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st) != cudaSuccess) {
+        set_error("b200vor_otm_newton: copy of the result failed");
+        return fail(B200VOR_ERR_CUDA);
+    }
+    B200_CUDA_CHECK(cudaStreamSynchronize(st));
+    if(res) {
+        *res = R;
+    }
+    return B200VOR_OK;
+}
+
+}  // namespace b200vor

@@ -331,4 +331,66 @@ void CentroidalVoronoiTesselation::Lloyd_iterations(index_t nb_iter) {
     }
 }
 
+// ------------------------------------------------------------------ OptimalTransportMap3d
+OptimalTransportMap3d::OptimalTransportMap3d()
+    : ctx_(new_context()), epsilon_(0.01), converged_(false), newton_iters_(0) {}
+
+OptimalTransportMap3d::~OptimalTransportMap3d() { b200vor_destroy(ctx_); }
+
+void OptimalTransportMap3d::set_domain_box(const double* box6) {
+    check(b200vor_set_domain_box(ctx_, box6), "OptimalTransportMap3d::set_domain_box");
+}
+
+void OptimalTransportMap3d::set_periodic(double period) {
+    check(b200vor_set_domain_periodic(ctx_, period), "OptimalTransportMap3d::set_periodic");
+}
+
+void OptimalTransportMap3d::set_points(index_t nb_points, const double* points) {
+    points_.assign(points, points + 3 * size_t(nb_points));
+    weights_.assign(nb_points, 0.0);
+    nu_.clear();
+    converged_ = false;
+}
+
+void OptimalTransportMap3d::set_nu(index_t i, double nu) {
+    if(nu_.empty()) {
+        nu_.assign(weights_.size(), -1.0);
+    }
+    nu_[i] = nu;
+}
+
+void OptimalTransportMap3d::optimize(index_t max_iterations) {
+    const index_t n = nb_points();
+    if(n == 0) {
+        return;
+    }
+    for(size_t i = 0; i < nu_.size(); ++i) {
+        if(!(nu_[i] > 0.0)) {
+            throw std::runtime_error("OptimalTransportMap3d::optimize: set_nu must be called for every point or for none");
+        }
+    }
+    check(b200vor_set_points(ctx_, n, points_.data(), 3, nullptr, 0), "OptimalTransportMap3d::optimize (set_points)");
+    b200vor_otm_params p;
+    memset(&p, 0, sizeof(p));
+    p.max_newton = max_iterations;
+    p.epsilon = epsilon_;
+    b200vor_otm_result r;
+    check(b200vor_otm_newton(ctx_, nu_.empty() ? nullptr : nu_.data(), weights_.data(), &p, &r, 0),
+          "OptimalTransportMap3d::optimize");
+    converged_ = r.converged != 0;
+    newton_iters_ = r.newton_iters;
+    measure_.resize(n);
+    mg_.resize(3 * size_t(n));
+    check(b200vor_get_cells(ctx_, measure_.data(), mg_.data(), nullptr, 0), "OptimalTransportMap3d::optimize (get_cells)");
+}
+
+vec3 OptimalTransportMap3d::cell_centroid(index_t i) const {
+    vec3 r;
+    double s = 1.0 / measure_[i];
+    r.x = s * mg_[3 * size_t(i)];
+    r.y = s * mg_[3 * size_t(i) + 1];
+    r.z = s * mg_[3 * size_t(i) + 2];
+    return r;
+}
+
 }  // namespace B200GEO

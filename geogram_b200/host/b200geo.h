@@ -179,6 +179,40 @@ private:
     std::vector<bool> point_is_locked_;
 };
 
+/* Semi-discrete optimal transport between the uniform measure of the domain (unit cube, a box or
+   a periodic cube) and weighted Dirac masses at the points.  Mirrors the part of
+   OptimalTransportMap3d (BrunoLevy/exploragram, not in the reference tree) that its callers use
+   (src/examples/exploragram/compute_OTM/main.cpp:284-297): set_points, set_epsilon, optimize,
+   weight().  The domain is a box instead of a tetrahedral mesh. */
+class OptimalTransportMap3d {
+public:
+    OptimalTransportMap3d();
+    ~OptimalTransportMap3d();
+    void set_domain_box(const double* box6);
+    void set_periodic(double period);
+    void set_points(index_t nb_points, const double* points);
+    /* target measure of point i (default: |domain| / nb_points each) */
+    void set_nu(index_t i, double nu);
+    /* maximum relative measure error in a cell (OptimalTransportMap::set_epsilon) */
+    void set_epsilon(double eps) { epsilon_ = eps; }
+    /* damped Newton iterations on the weights, all on the device */
+    void optimize(index_t max_iterations);
+    index_t nb_points() const { return index_t(weights_.size()); }
+    double weight(index_t i) const { return weights_[i]; }
+    /* measure of the Laguerre cell of point i at the current weights */
+    double cell_measure(index_t i) const { return measure_[i]; }
+    vec3 cell_centroid(index_t i) const;
+    bool converged() const { return converged_; }
+    index_t nb_newton_iterations() const { return newton_iters_; }
+
+private:
+    b200vor_ctx* ctx_;
+    std::vector<double> points_, weights_, nu_, measure_, mg_;
+    double epsilon_;
+    bool converged_;
+    index_t newton_iters_;
+};
+
 }  // namespace B200GEO
 
 #endif

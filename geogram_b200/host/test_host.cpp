@@ -180,6 +180,22 @@ int main() {
         cvt.funcgrad(3 * n, x2.data(), f2, g2.data());
         EXPECT(fabs((f0 - f2) / h - gg) < 0.05 * gg);
     }
+    // ---- OptimalTransportMap3d: uniform target on the box, every cell reaches 1/n
+    {
+        OptimalTransportMap3d otm;
+        otm.set_points(n, cvt.embedding(0));
+        otm.set_epsilon(1e-4);
+        otm.optimize(30);
+        EXPECT(otm.converged());
+        double worst = 0.0, total = 0.0;
+        for(index_t i = 0; i < n; ++i) {
+            worst = std::max(worst, fabs(otm.cell_measure(i) * n - 1.0));
+            total += otm.cell_measure(i);
+        }
+        EXPECT(worst <= 1e-4);
+        EXPECT(fabs(total - 1.0) < 1e-9);
+        EXPECT(otm.nb_newton_iterations() > 0 && otm.nb_newton_iterations() < 30);
+    }
     printf(fails ? "host test: %d FAILURES\n" : "host test: ok\n", fails);
     return fails ? 1 : 0;
 }

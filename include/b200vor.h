@@ -28,6 +28,8 @@
  *                                                                   voronoi/RVD.h:284-290
  *   b200vor_get_faces        ConvexCell::v_global_index / facet_area voronoi/convex_cell.h:463, convex_cell.cpp:1160
  *   b200vor_get_cvt          ComputeCVTFuncGradVolumetric (f, g)    voronoi/RVD.cpp:791-876
+ *   b200vor_otm_newton       [external] OptimalTransportMap3d::optimize (exploragram; call sites
+ *                            src/examples/exploragram/compute_OTM/main.cpp:284-297)
  *   b200vor_lloyd            CentroidalVoronoiTesselation::Lloyd_iterations
  *                                                                   voronoi/CVT.cpp:133-169
  */
@@ -136,6 +138,35 @@ int b200vor_get_faces(b200vor_ctx* ctx, uint32_t* nfaces, uint32_t* face_nbr,
  *   f_total    sum of f_i in a fixed order (deterministic)
  * any output may be NULL; f_total is always a host pointer */
 int b200vor_get_cvt(b200vor_ctx* ctx, double* f_cell, double* g, double* f_total, int on_device);
+
+/* ---- semi-discrete optimal transport: damped Newton on the Laguerre weights ----
+ * Finds w such that vol(Lag_i(w)) = nu_i for the points of b200vor_set_points in the current
+ * domain.  Stands in for OptimalTransportMap3d::optimize (BrunoLevy/exploragram, not part of
+ * the reference tree; call sites src/examples/exploragram/compute_OTM/main.cpp:284-297) and
+ * restates the published algorithm: gradient vol_i - nu_i and Hessian A_ij / (2 |p_i - p_j|)
+ * (Levy 2015), damping of Kitagawa-Merigot-Thibert 2019 (Algorithm 1), linear systems by
+ * Jacobi-preconditioned conjugate gradient on the device. */
+typedef struct b200vor_otm_params {
+    uint32_t max_newton;  /* 0 = 50                                                        */
+    uint32_t max_cg;      /* CG iterations per Newton step, 0 = 1000                       */
+    double cg_tol;        /* relative residual of the linear solve, 0 = 1e-8               */
+    double epsilon;       /* stop when max_i |vol_i - nu_i| <= epsilon * nu_i, 0 = 0.01
+                             (OptimalTransportMap::set_epsilon)                            */
+    double total_mass;    /* nu == NULL: nu_i = total_mass / n, 0 = measure of the domain  */
+} b200vor_otm_params;
+
+typedef struct b200vor_otm_result {
+    uint32_t newton_iters, cg_iters, cell_evals;
+    int32_t converged;
+    double initial_error, final_error;   /* || vol - nu ||_2 before / after                */
+    double max_rel_error;                /* max_i |vol_i - nu_i| / nu_i                    */
+    double min_volume, sum_volume, last_alpha;
+} b200vor_otm_result;
+
+/* nu: n target measures or NULL (uniform); w: n weights, start values in, solution out.  The cells
+ * (b200vor_get_cells / b200vor_get_faces) are those of the returned weights. */
+int b200vor_otm_newton(b200vor_ctx* ctx, const double* nu, double* w, const b200vor_otm_params* params,
+                       b200vor_otm_result* result, int on_device);
 
 /* ---- Lloyd relaxation: iters x (grid, cells, p <- mg/m, periodic wrap) ---- */
 /* xyz_out (n x 3, may be NULL) receives the relaxed points */

@@ -280,6 +280,67 @@ def test_cvt_energy_and_gradient(Context, port, periodic):
     ctx.close()
 
 
+# ---------------------------------------------------------------- semi-discrete OT (a20 / 8(f) rank 1)
+@pytest.mark.parametrize("periodic", [True, False])
+def test_otm_newton_vs_cpu_restatement(Context, port, periodic):
+    """Damped Newton on the Laguerre weights (Levy 2015 + KMT 2019) on the device against the CPU
+    restatement oracle/otm_oracle.py (exact cells from the oracle port, sparse direct solves):
+    same number of Newton steps, same weights up to the additive constant, prescribed volumes
+    reached.  exploragram itself is absent: parity-unpinned, see DESIGN.md section 2."""
+    import sys
+    sys.path.insert(0, os.path.join(oracles.ROOT, "oracle"))
+    import otm_oracle
+    n = 20000
+    xyz = oracles.uniform_seeds(n, 31)
+    ctx = Context(0)
+    if periodic:
+        ctx.set_domain_periodic(1.0)
+    ctx.set_points(xyz)
+    xyz = ctx.lloyd(3)                       # no empty Laguerre cells at w = 0 is all KMT needs
+    nu = 0.5 + np.random.default_rng(1).random(n)
+    nu /= nu.sum()
+    ctx.set_points(xyz)
+    w, res = ctx.otm_newton(nu, epsilon=1e-6, cg_tol=1e-11, max_cg=5000)
+    assert res["converged"] == 1 and res["max_rel_error"] <= 1e-6
+    assert abs(res["sum_volume"] - 1.0) < SUM_TOL
+    m, mg, st = ctx.get_cells()              # the cells of the returned weights
+    assert (st == 0).all()
+    assert np.abs(m - nu).max() <= 1e-6 * nu.min() * 1.0001 + 1e-18 or (np.abs(m - nu) / nu).max() <= 1e-6
+    w_cpu, R, log = otm_oracle.otm_newton(port, xyz, nu, periodic=periodic, epsilon=1e-6)
+    assert res["newton_iters"] == len(log)
+    assert res["last_alpha"] == log[-1][0]
+    dw = (w - w.mean()) - (w_cpu - w_cpu.mean())
+    scale = np.abs(w_cpu - w_cpu.mean()).max()
+    assert np.abs(dw).max() <= 1e-6 * scale
+    # cross-check: the CPU cells of the GPU weights have the prescribed volumes
+    C = port.cells(xyz, w=w, periodic=periodic, kcap=2000)
+    assert (np.abs(C.m - nu) / nu).max() <= 2e-6
+    ctx.close()
+
+
+def test_otm_newton_uniform_10m_property(Context):
+    """BASELINE configs[2] at a size the GPU finishes in seconds (2M): uniform target measure on
+    Lloyd-relaxed seeds with random start weights a = 0.25 h^2 U(0,1); the solve must bring every
+    cell to 1/n within epsilon, keep the total volume, and be bitwise reproducible."""
+    n = 2000000
+    xyz = oracles.uniform_seeds(n, 12345)
+    ctx = Context(0)
+    ctx.set_domain_periodic(1.0)
+    ctx.set_points(xyz)
+    xyz = ctx.lloyd(5)
+    h = n ** (-1.0 / 3.0)
+    w0 = 0.25 * h * h * np.random.default_rng(5).random(n)
+    ctx.set_points(xyz)
+    w, res = ctx.otm_newton(None, w0=w0, epsilon=1e-3)
+    assert res["converged"] == 1 and res["max_rel_error"] <= 1e-3
+    assert abs(res["sum_volume"] - 1.0) < SUM_TOL and res["min_volume"] > 0.5 / n
+    m, _, st = ctx.get_cells()
+    assert (st == 0).all() and (np.abs(m * n - 1.0)).max() <= 1e-3
+    w2, res2 = ctx.otm_newton(None, w0=w0, epsilon=1e-3)
+    assert (w == w2).all() and res2["cg_iters"] == res["cg_iters"]
+    ctx.close()
+
+
 # ---------------------------------------------------------------- the two cell pipelines
 @pytest.mark.parametrize("periodic,weighted", [(False, False), (True, False), (True, True)])
 def test_fused_walk_equals_knn_table_pipeline(Context, periodic, weighted):

@@ -51,6 +51,23 @@ def main():
                    ms_grid=s["ms_grid"], ms_knn=s["ms_knn"], ms_clip=s["ms_clip"],
                    cells_per_s=n / (1e-3 * s["ms_total"]), passes=s["n_pass"][: s["passes"]],
                    k_pass=s["k_pass"][: s["passes"]])
+    elif kind == "otm":
+        # config 3, full solve: uniform target on relaxed seeds, random start weights
+        iters = int(sys.argv[3]) if len(sys.argv) > 3 else 5
+        eps = float(sys.argv[4]) if len(sys.argv) > 4 else 1e-3
+        xyz = oracles.uniform_seeds(n, 12345)
+        ctx.set_domain_periodic(1.0)
+        ctx.set_points(xyz)
+        xyz = ctx.lloyd(iters)
+        h = n ** (-1.0 / 3.0)
+        w0 = 0.25 * h * h * np.random.default_rng(5).random(n)
+        ctx.set_points(xyz)
+        t0 = time.perf_counter()
+        w, r = ctx.otm_newton(None, w0=w0, epsilon=eps)
+        res["wall_s_otm_newton"] = time.perf_counter() - t0
+        s = ctx.stats()
+        res.update(r)
+        res.update(ms_grid=s["ms_grid"], ms_clip=s["ms_clip"], ms_knn=s["ms_knn"])
     else:
         kmax = int(sys.argv[3]) if len(sys.argv) > 3 else 0
         mode = int(sys.argv[4]) if len(sys.argv) > 4 else 0
