@@ -27,7 +27,7 @@ EXPORTS = [
     "b200vor_version", "b200vor_last_error", "b200vor_create", "b200vor_destroy",
     "b200vor_set_domain_box", "b200vor_set_domain_periodic", "b200vor_set_points",
     "b200vor_knn", "b200vor_knn_points", "b200vor_compute_cells", "b200vor_get_cells",
-    "b200vor_get_faces", "b200vor_get_cvt", "b200vor_otm_newton", "b200vor_lloyd", "b200vor_get_stats",
+    "b200vor_get_faces", "b200vor_get_vertices", "b200vor_get_cvt", "b200vor_otm_newton", "b200vor_lloyd", "b200vor_get_stats",
     "b200vor_set_points_per_cell", "b200vor_set_stream", "b200vor_set_query_range",
 ]
 
@@ -111,6 +111,7 @@ def load_library():
     lib.b200vor_compute_cells.argtypes = [vp, ctypes.POINTER(CellParams)]
     lib.b200vor_get_cells.argtypes = [vp, vp, vp, vp, i32]
     lib.b200vor_get_faces.argtypes = [vp, vp, vp, vp, u32, i32]
+    lib.b200vor_get_vertices.argtypes = [vp, vp, vp, vp, u32, i32]
     lib.b200vor_get_cvt.argtypes = [vp, vp, vp, ctypes.POINTER(dbl), i32]
     lib.b200vor_otm_newton.argtypes = [vp, vp, vp, ctypes.POINTER(OtmParams), ctypes.POINTER(OtmResult), i32]
     lib.b200vor_lloyd.argtypes = [vp, u32, ctypes.POINTER(CellParams), vp, i32]
@@ -208,8 +209,8 @@ class Context(object):
 
     # ---- cells ----
     def compute_cells(self, k0=0, kmax=0, want_faces=False, mode=0, want_energy=False):
-        p = CellParams(int(k0), int(kmax), 1 if want_faces else 0, int(mode),
-                       1 if want_energy else 0)
+        # want_faces: False / True (face lists) / 2 (face lists + cell vertices)
+        p = CellParams(int(k0), int(kmax), int(want_faces), int(mode), 1 if want_energy else 0)
         self._check(self.lib.b200vor_compute_cells(self.h, ctypes.byref(p)))
 
     def get_cells(self):
@@ -230,6 +231,16 @@ class Context(object):
         area = np.zeros((self.n, FCAP))
         self._check(self.lib.b200vor_get_faces(self.h, _ptr(nf), _ptr(nbr), _ptr(area), FCAP, 0))
         return nf, nbr, area
+
+    def get_vertices(self):
+        """(nverts[n], xyz[n,64,3], faces[n,64,3]) of compute_cells(want_faces=2): cell vertices and,
+        per vertex, the positions in the face list of the three faces that meet there."""
+        nv = np.zeros(self.n, np.uint32)
+        xyz = np.zeros((self.n, FCAP, 3))
+        vf = np.zeros((self.n, FCAP), np.uint32)
+        self._check(self.lib.b200vor_get_vertices(self.h, _ptr(nv), _ptr(xyz), _ptr(vf), FCAP, 0))
+        faces = np.stack([vf & 0xFF, (vf >> 8) & 0xFF, (vf >> 16) & 0xFF], axis=-1).astype(np.uint8)
+        return nv, xyz, faces
 
     def get_cvt(self):
         """(f_total, f_cell[n], g[n,3]) of the CVT objective (RVD.cpp:791-876); needs

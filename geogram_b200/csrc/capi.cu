@@ -161,6 +161,14 @@ int cells_pipeline(Ctx* c, const b200vor_cell_params* params, bool collect_event
             return rc;
         }
     }
+    if(p.want_faces == 2) {
+        if((rc = c->nverts.reserve(n)) || (rc = c->vert_xyz.reserve(size_t(n) * c->vcap * 3)) ||
+           (rc = c->vert_faces.reserve(size_t(n) * c->vcap))) {
+            return rc;
+        }
+        // cells finished by the kNN-table pipeline have no vertex list: nverts = 0xFFFFFFFF
+        B200_CUDA_CHECK(cudaMemsetAsync(c->nverts.p, 0xFF, size_t(n) * sizeof(uint32_t), c->stream));
+    }
     if(p.want_energy && (rc = c->energy.reserve(n))) {
         return rc;
     }
@@ -298,6 +306,7 @@ int cells_pipeline(Ctx* c, const b200vor_cell_params* params, bool collect_event
     c->cells_valid = true;
     c->faces_valid = p.want_faces != 0;
     c->energy_valid = p.want_energy != 0;
+    c->verts_valid = p.want_faces == 2;
     return B200VOR_OK;
 }
 
@@ -381,7 +390,7 @@ void b200vor_destroy(b200vor_ctx* h) {
     c.cell_start.release(); c.perm.release(); c.scan_tmp.release(); c.sorted.release();
     c.knn.release(); c.knn_flag.release(); c.qlist.release(); c.qlist2.release(); c.qlist3.release(); c.qrows.release();
     c.counter.release(); c.m.release(); c.mg.release(); c.status.release();
-    c.energy.release(); c.nfaces.release(); c.face_nbr.release(); c.face_area.release(); c.evcount.release();
+    c.energy.release(); c.nverts.release(); c.vert_xyz.release(); c.vert_faces.release(); c.nfaces.release(); c.face_nbr.release(); c.face_area.release(); c.evcount.release();
     c.sums.release(); c.out_nbr.release(); c.out_d2.release(); c.qpts.release();
     if(c.own_stream) {
         cudaStreamDestroy(c.stream);
@@ -691,6 +700,29 @@ int b200vor_get_cvt(b200vor_ctx* h, double* f_cell, double* g, double* f_total, 
             t += hp[b];
         }
         *f_total = t;
+    }
+    B200_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return B200VOR_OK;
+}
+
+int b200vor_get_vertices(b200vor_ctx* h, uint32_t* nverts, double* vert_xyz, uint32_t* vert_faces,
+                         uint32_t vcap, int on_device) {
+    if(!h || !h->c.cells_valid || !h->c.verts_valid) {
+        set_error("b200vor_get_vertices: cells were not computed with want_faces=2");
+        return B200VOR_ERR_ARG;
+    }
+    Ctx* c = &h->c;
+    if(vcap != c->vcap) {
+        set_error("b200vor_get_vertices: vcap must be %u", c->vcap);
+        return B200VOR_ERR_ARG;
+    }
+    B200_CUDA_CHECK(cudaSetDevice(c->device));
+    int rc;
+    size_t cnt = size_t(c->n) * vcap;
+    if((nverts && (rc = copy_out(nverts, c->nverts.p, size_t(c->n) * sizeof(uint32_t), on_device, c->stream))) ||
+       (vert_xyz && (rc = copy_out(vert_xyz, c->vert_xyz.p, cnt * 3 * sizeof(double), on_device, c->stream))) ||
+       (vert_faces && (rc = copy_out(vert_faces, c->vert_faces.p, cnt * sizeof(uint32_t), on_device, c->stream)))) {
+        return rc;
     }
     B200_CUDA_CHECK(cudaStreamSynchronize(c->stream));
     return B200VOR_OK;

@@ -138,6 +138,11 @@ struct Ctx {
     DevBuf<uint32_t> nfaces, face_nbr;
     DevBuf<double> face_area;
     uint32_t fcap = 0;
+    // per-cell vertex lists (want_faces == 2): nverts[n], vert_xyz[n*vcap*3], vert_faces[n*vcap]
+    DevBuf<uint32_t> nverts, vert_faces;
+    DevBuf<double> vert_xyz;
+    uint32_t vcap = 64;
+    bool verts_valid = false;
     bool cells_valid = false, faces_valid = false;
     DevBuf<uint32_t> evcount;        // per-cell event counts (2 words)
     DevBuf<unsigned long long> sums; // reductions

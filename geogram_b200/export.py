@@ -1,0 +1,114 @@
+"""Host-side cell export from the GPU buffers.
+
+Inputs are the arrays of ``Context.get_faces()`` and ``Context.get_vertices()`` after
+``compute_cells(want_faces=2)``:
+
+* ``cell_loops``      -- the facets of one cell as oriented vertex loops (what
+                         ``ConvexCell::save`` walks through ``triangle_adjacent``,
+                         voronoi/convex_cell.cpp:334-346)
+* ``save_cells_obj``  -- ``PeriodicDelaunay3d::save_cells`` / ``ConvexCell::save``
+                         (delaunay/periodic_delaunay_3d.cpp:4363-4392, convex_cell.cpp:282-352):
+                         one Wavefront OBJ with every cell shrunk towards its centroid
+* ``delaunay_tets``   -- the Delaunay tetrahedra (``Delaunay::cell_vertex``, delaunay/delaunay.h:336-485):
+                         one per cell vertex = the seed and the three neighbours whose faces meet there
+
+Pure index bookkeeping on the host; the geometry (vertex coordinates, face lists) was computed on
+the device.
+"""
+import numpy as np
+
+BOX_ID = 0xFFFFFFF0
+NOT_AVAILABLE = 0xFFFFFFFF
+
+
+def cell_loops(nv, faces, nf):
+    """Facets of one cell.  nv: number of vertices, faces: (>=nv, 3) positions in the face list of
+    the three faces meeting at each vertex (same orientation for all vertices), nf: number of faces.
+    Returns a list of nf loops (lists of vertex indices, consistently oriented)."""
+    by_face = [[] for _ in range(nf)]
+    for v in range(nv):
+        a, b, c = (int(x) for x in faces[v])
+        # rotations of the triple with each face first: (f, next, prev)
+        by_face[a].append((v, b, c))
+        by_face[b].append((v, c, a))
+        by_face[c].append((v, a, b))
+    loops = []
+    for f in range(nf):
+        ring = by_face[f]
+        if len(ring) < 3:
+            loops.append([v for v, _, _ in ring])
+            continue
+        # the vertex after (v, g, h) around f is the one that enters through h: (v', h, *)
+        enter = {g: (v, h) for v, g, h in ring}
+        v0, g0, h0 = ring[0]
+        loop, h = [v0], h0
+        while len(loop) < len(ring):
+            if h not in enter:
+                break
+            v, h = enter[h]
+            if v == v0:
+                break
+            loop.append(v)
+        loops.append(loop)
+    return loops
+
+
+def _available(nverts, vcap):
+    return (nverts != NOT_AVAILABLE) & (nverts > 0) & (nverts <= vcap)
+
+
+def cell_volume_from_loops(xyz, loops, seed):
+    """Volume of a cell from its exported geometry (fan of tetrahedra with the seed as apex):
+    a check of vertex coordinates AND loop combinatorics."""
+    vol = 0.0
+    for loop in loops:
+        if len(loop) < 3:
+            continue
+        p0 = xyz[loop[0]] - seed
+        for k in range(1, len(loop) - 1):
+            vol += np.dot(p0, np.cross(xyz[loop[k]] - seed, xyz[loop[k + 1]] - seed))
+    return abs(vol) / 6.0
+
+
+def save_cells_obj(path, nverts, vert_xyz, vert_faces, nfaces, m, mg, shrink=0.1, cells=None):
+    """One OBJ file with every listed cell, each shrunk by `shrink` towards its centroid
+    (ConvexCell::save: p <- shrink*g + (1-shrink)*p).  Returns (#vertices, #facets) written."""
+    vcap = vert_xyz.shape[1]
+    ok = _available(nverts, vcap)
+    if cells is None:
+        cells = np.nonzero(ok)[0]
+    v_off, nfac = 1, 0
+    with open(path, "w") as out:
+        for i in cells:
+            if not ok[i]:
+                continue
+            nv = int(nverts[i])
+            g = mg[i] / m[i]
+            P = shrink * g + (1.0 - shrink) * vert_xyz[i, :nv]
+            for p in P:
+                out.write("v %.17g %.17g %.17g\n" % (p[0], p[1], p[2]))
+            for loop in cell_loops(nv, vert_faces[i], int(nfaces[i])):
+                if len(loop) >= 3:
+                    out.write("f " + " ".join(str(v + v_off) for v in loop) + "\n")
+                    nfac += 1
+            v_off += nv
+    return v_off - 1, nfac
+
+
+def delaunay_tets(nverts, vert_faces, nfaces, face_nbr, n):
+    """Delaunay tetrahedra as an (nt, 4) uint32 array of vertex ids (periodic: real + n*instance, as
+    PeriodicDelaunay3d numbers translated copies).  A tetrahedron is reported by the cell of its
+    smallest real vertex index; vertices on the clipping box belong to no tetrahedron."""
+    vcap = vert_faces.shape[1]
+    ok = _available(nverts, vcap)
+    idx = np.arange(vcap)[None, :]
+    valid = ok[:, None] & (idx < nverts[:, None])
+    rows = np.nonzero(valid)
+    f = vert_faces[rows].astype(np.int64)                     # (K, 3) face positions
+    nb = face_nbr[rows[0][:, None], f].astype(np.int64)       # (K, 3) neighbour ids
+    interior = (nb < BOX_ID).all(axis=1)
+    seed = rows[0][interior]
+    nb = nb[interior]
+    keep = (seed[:, None] < (nb % n)).all(axis=1)
+    tets = np.concatenate([seed[keep][:, None], nb[keep]], axis=1)
+    return tets.astype(np.uint32)

@@ -27,6 +27,9 @@
  *   b200vor_get_cells        RestrictedVoronoiDiagram::compute_centroids (mg, m)
  *                                                                   voronoi/RVD.h:284-290
  *   b200vor_get_faces        ConvexCell::v_global_index / facet_area voronoi/convex_cell.h:463, convex_cell.cpp:1160
+ *   b200vor_get_vertices     ConvexCell::triangle_point / save      voronoi/convex_cell.h:888, convex_cell.cpp:282-352
+ *                            PeriodicDelaunay3d::save_cells         delaunay/periodic_delaunay_3d.cpp:4363-4392
+ *                            Delaunay::cell_vertex (tetrahedra)     delaunay/delaunay.h:336-485
  *   b200vor_get_cvt          ComputeCVTFuncGradVolumetric (f, g)    voronoi/RVD.cpp:791-876
  *   b200vor_otm_newton       [external] OptimalTransportMap3d::optimize (exploragram; call sites
  *                            src/examples/exploragram/compute_OTM/main.cpp:284-297)
@@ -70,7 +73,8 @@ typedef struct b200vor_ctx b200vor_ctx;
 typedef struct b200vor_cell_params {
     uint32_t k0;          /* neighbours fetched in the first pass (0 = default 48)            */
     uint32_t kmax;        /* cap on k for the re-launches of uncertified cells (0 = 384)      */
-    uint32_t want_faces;  /* 1: keep per-cell face lists (+ areas) for b200vor_get_faces      */
+    uint32_t want_faces;  /* 1: keep per-cell face lists (+ areas) for b200vor_get_faces;
+                             2: also the cell vertices for b200vor_get_vertices               */
     uint32_t mode;        /* 0 = fused grid walk (no kNN table); the cells it flags UNCERTIFIED /
                                  OVERFLOW are re-done by the kNN-table pipeline
                              1 = fused grid walk only (flags are left on the cells)
@@ -130,6 +134,18 @@ int b200vor_get_cells(b200vor_ctx* ctx, double* m, double* mg, uint8_t* status, 
 /* nfaces[n], face_nbr[n*fcap] (ascending ids), face_area[n*fcap] (may be NULL) */
 int b200vor_get_faces(b200vor_ctx* ctx, uint32_t* nfaces, uint32_t* face_nbr,
                       double* face_area, uint32_t fcap, int on_device);
+
+/* cell geometry of the last b200vor_compute_cells(want_faces=2), what ConvexCell::save
+ * (voronoi/convex_cell.cpp:282-352), append_to_mesh (:371-444) and the Delaunay tetrahedra
+ * (one per cell vertex: the seed and the three neighbours whose faces meet there) are built from:
+ *   nverts[n]            vertices of the cell (0: empty/duplicate; 0xFFFFFFFF: not available, the
+ *                        cell was finished by the kNN-table pipeline; > vcap: list truncated)
+ *   vert_xyz[n*vcap*3]   ConvexCell::triangle_point, absolute coordinates (periodic: around the seed)
+ *   vert_faces[n*vcap]   f0 | f1 << 8 | f2 << 16: positions in the cell's face list (b200vor_get_faces)
+ *                        of the three faces meeting at the vertex, same orientation for all vertices
+ * vcap must be 64. */
+int b200vor_get_vertices(b200vor_ctx* ctx, uint32_t* nverts, double* vert_xyz, uint32_t* vert_faces,
+                         uint32_t vcap, int on_device);
 
 /* CVT objective of the last b200vor_compute_cells(want_energy=1)
  * (ComputeCVTFuncGradVolumetric, voronoi/RVD.cpp:791-876, summed per seed):
