@@ -5,6 +5,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <fstream>
+
 #include <algorithm>
 #include <stdexcept>
 
@@ -211,11 +213,13 @@ void ConvexCellBatch::set_periodic(double period) {
     check(b200vor_set_domain_periodic(ctx_, period), "ConvexCellBatch::set_periodic");
 }
 
-void ConvexCellBatch::compute(index_t nb_seeds, const double* xyz, const double* weights, bool with_faces) {
+void ConvexCellBatch::compute(index_t nb_seeds, const double* xyz, const double* weights, bool with_faces,
+                              bool with_vertices) {
     check(b200vor_set_points(ctx_, nb_seeds, xyz, 3, weights, 0), "ConvexCellBatch::compute (set_points)");
     b200vor_cell_params p;
     memset(&p, 0, sizeof(p));
-    p.want_faces = with_faces ? 1 : 0;
+    with_faces = with_faces || with_vertices;
+    p.want_faces = with_vertices ? 2 : (with_faces ? 1 : 0);
     check(b200vor_compute_cells(ctx_, &p), "ConvexCellBatch::compute");
     m_.resize(nb_seeds);
     mg_.resize(3 * size_t(nb_seeds));
@@ -231,6 +235,138 @@ void ConvexCellBatch::compute(index_t nb_seeds, const double* xyz, const double*
         nfaces_.clear();
         face_nbr_.clear();
         face_area_.clear();
+    }
+    if(with_vertices) {
+        nverts_.resize(nb_seeds);
+        vert_xyz_.resize(size_t(nb_seeds) * 64 * 3);
+        vert_faces_.resize(size_t(nb_seeds) * 64);
+        check(b200vor_get_vertices(ctx_, nverts_.data(), vert_xyz_.data(), vert_faces_.data(), 64, 0),
+              "ConvexCellBatch::compute (get_vertices)");
+    } else {
+        nverts_.clear();
+        vert_xyz_.clear();
+        vert_faces_.clear();
+    }
+}
+
+index_t ConvexCellBatch::nb_t(index_t c) const {
+    if(nverts_.empty() || nverts_[c] == 0xFFFFFFFFu || nverts_[c] > 64) {
+        return 0;   // not available (kNN-table pipeline) or more vertices than the list holds
+    }
+    return nverts_[c];
+}
+
+vec3 ConvexCellBatch::triangle_point(index_t c, index_t t) const {
+    const double* p = &vert_xyz_[(size_t(c) * 64 + t) * 3];
+    vec3 r = {p[0], p[1], p[2]};
+    return r;
+}
+
+index_t ConvexCellBatch::triangle_v_local_index(index_t c, index_t t, index_t lv) const {
+    return (vert_faces_[size_t(c) * 64 + t] >> (8 * lv)) & 0xFFu;
+}
+
+void ConvexCellBatch::facet_loops(index_t c, std::vector<std::vector<index_t> >& loops) const {
+    const index_t nt = nb_t(c), nf = nb_v(c);
+    loops.assign(nf, std::vector<index_t>());
+    // per face: for every vertex on it, (vertex, face it is entered through, face it is left through);
+    // all triples have the same orientation, so the vertex after (v, g, h) is the one entered through h
+    std::vector<std::vector<index_t> > ring(nf);
+    for(index_t t = 0; t < nt; ++t) {
+        for(index_t l = 0; l < 3; ++l) {
+            ring[triangle_v_local_index(c, t, l)].push_back(t * 3 + l);
+        }
+    }
+    for(index_t f = 0; f < nf; ++f) {
+        const std::vector<index_t>& R = ring[f];
+        if(R.empty()) {
+            continue;
+        }
+        std::vector<index_t>& L = loops[f];
+        index_t cur = R[0];
+        for(size_t step = 0; step < R.size(); ++step) {
+            const index_t t = cur / 3, l = cur % 3;
+            L.push_back(t);
+            const index_t h = triangle_v_local_index(c, t, (l + 2) % 3);
+            bool found = false;
+            for(size_t k = 0; k < R.size() && !found; ++k) {
+                const index_t t2 = R[k] / 3, l2 = R[k] % 3;
+                if(t2 != t && triangle_v_local_index(c, t2, (l2 + 1) % 3) == h) {
+                    cur = R[k];
+                    found = true;
+                }
+            }
+            if(!found || cur == R[0]) {
+                break;
+            }
+        }
+    }
+}
+
+index_t ConvexCellBatch::save(index_t c, std::ostream& out, global_index_t v_offset, double shrink) const {
+    const index_t nt = nb_t(c);
+    if(nt == 0) {
+        return 0;
+    }
+    vec3 g = {0.0, 0.0, 0.0};
+    if(shrink != 0.0) {
+        g = barycenter(c);
+    }
+    out.precision(17);
+    for(index_t t = 0; t < nt; ++t) {
+        vec3 p = triangle_point(c, t);
+        if(shrink != 0.0) {
+            p.x = shrink * g.x + (1.0 - shrink) * p.x;
+            p.y = shrink * g.y + (1.0 - shrink) * p.y;
+            p.z = shrink * g.z + (1.0 - shrink) * p.z;
+        }
+        out << "v " << p.x << " " << p.y << " " << p.z << std::endl;
+    }
+    std::vector<std::vector<index_t> > loops;
+    facet_loops(c, loops);
+    for(size_t f = 0; f < loops.size(); ++f) {
+        if(loops[f].size() < 3) {
+            continue;
+        }
+        out << "f ";
+        for(size_t k = 0; k < loops[f].size(); ++k) {
+            out << (loops[f][k] + v_offset) << " ";
+        }
+        out << std::endl;
+    }
+    return nt;
+}
+
+void ConvexCellBatch::save_cells(const std::string& filename, double shrink) const {
+    std::ofstream out(filename.c_str());
+    if(!out) {
+        throw std::runtime_error("ConvexCellBatch::save_cells: cannot open " + filename);
+    }
+    global_index_t v_off = 1;
+    for(index_t c = 0; c < nb_cells(); ++c) {
+        v_off += save(c, out, v_off, shrink);
+    }
+}
+
+void ConvexCellBatch::delaunay_tetrahedra(std::vector<global_index_t>& tets) const {
+    tets.clear();
+    const index_t n = nb_cells();
+    for(index_t c = 0; c < n; ++c) {
+        const index_t nt = nb_t(c);
+        for(index_t t = 0; t < nt; ++t) {
+            global_index_t v[3];
+            bool keep = true;
+            for(index_t l = 0; l < 3 && keep; ++l) {
+                v[l] = v_global_index(c, triangle_v_local_index(c, t, l));
+                keep = v[l] < BOX_ID && c < v[l] % n;   // reported by the smallest real index
+            }
+            if(keep) {
+                tets.push_back(c);
+                tets.push_back(v[0]);
+                tets.push_back(v[1]);
+                tets.push_back(v[2]);
+            }
+        }
     }
 }
 

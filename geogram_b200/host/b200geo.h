@@ -24,6 +24,7 @@
 #include <stdint.h>
 
 #include <mutex>
+#include <ostream>
 #include <string>
 #include <vector>
 
@@ -128,7 +129,8 @@ public:
     /* periodic cube [0,period)^3: neighbour ids are real + N*instance (periodic.h:95-99) */
     void set_periodic(double period);
     /* weights may be null (Voronoi) */
-    void compute(index_t nb_seeds, const double* xyz, const double* weights, bool with_faces = true);
+    void compute(index_t nb_seeds, const double* xyz, const double* weights, bool with_faces = true,
+                 bool with_vertices = false);
 
     index_t nb_cells() const { return index_t(m_.size()); }
     bool empty(index_t c) const { return (status_[c] & 4u) != 0; }
@@ -142,11 +144,29 @@ public:
     double facet_area(index_t c, index_t lv) const { return face_area_[size_t(c) * 64 + lv]; }
     double total_volume() const;
 
+    /* ---- cell geometry (compute(..., with_vertices = true)), names of VBW::ConvexCell ---- */
+    /* number of cell vertices = dual triangles (ConvexCell::nb_t); 0 when not available */
+    index_t nb_t(index_t c) const;
+    /* ConvexCell::triangle_point (convex_cell.h:888) */
+    vec3 triangle_point(index_t c, index_t t) const;
+    /* the three faces meeting at vertex t, as local face indices lv (ConvexCell::triangle_v_local_index) */
+    index_t triangle_v_local_index(index_t c, index_t t, index_t lv) const;
+    /* facets of the cell as oriented vertex loops, one per local face index */
+    void facet_loops(index_t c, std::vector<std::vector<index_t> >& loops) const;
+    /* ConvexCell::save (convex_cell.cpp:282-352): "v"/"f" records, vertices shrunk towards the
+       centroid; returns the number of vertices written */
+    index_t save(index_t c, std::ostream& out, global_index_t v_offset = 1, double shrink = 0.0) const;
+    /* PeriodicDelaunay3d::save_cells (periodic_delaunay_3d.cpp:4363-4392): every cell, shrink 0.1 */
+    void save_cells(const std::string& filename, double shrink = 0.1) const;
+    /* Delaunay tetrahedra (Delaunay::cell_vertex, delaunay.h:336-485): 4 vertex ids each
+       (periodic: real + N*instance), every tetrahedron once */
+    void delaunay_tetrahedra(std::vector<global_index_t>& tets) const;
+
 private:
     b200vor_ctx* ctx_;
-    std::vector<double> m_, mg_, face_area_;
+    std::vector<double> m_, mg_, face_area_, vert_xyz_;
     std::vector<uint8_t> status_;
-    std::vector<uint32_t> nfaces_, face_nbr_;
+    std::vector<uint32_t> nfaces_, face_nbr_, nverts_, vert_faces_;
 };
 
 class CentroidalVoronoiTesselation {

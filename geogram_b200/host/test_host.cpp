@@ -180,6 +180,60 @@ int main() {
         cvt.funcgrad(3 * n, x2.data(), f2, g2.data());
         EXPECT(fabs((f0 - f2) / h - gg) < 0.05 * gg);
     }
+    // ---- cell geometry export: loops close, volume from the exported geometry, tetrahedra, OBJ
+    {
+        ConvexCellBatch pc;
+        pc.set_periodic(1.0);
+        pc.compute(n, pts.data(), nullptr, true, true);
+        size_t sum_t = 0;
+        double worst = 0.0;
+        for(index_t c = 0; c < n; ++c) {
+            EXPECT(pc.nb_t(c) == 2 * pc.nb_v(c) - 4);
+            sum_t += pc.nb_t(c);
+            if(c % 13) {
+                continue;
+            }
+            std::vector<std::vector<index_t> > loops;
+            pc.facet_loops(c, loops);
+            double vol6 = 0.0;
+            const double* s0 = &pts[3 * size_t(c)];
+            for(size_t f = 0; f < loops.size(); ++f) {
+                EXPECT(loops[f].size() >= 3);
+                vec3 a = pc.triangle_point(c, loops[f][0]);
+                for(size_t k = 1; k + 1 < loops[f].size(); ++k) {
+                    vec3 b = pc.triangle_point(c, loops[f][k]), d = pc.triangle_point(c, loops[f][k + 1]);
+                    double A[3] = {a.x - s0[0], a.y - s0[1], a.z - s0[2]};
+                    double B[3] = {b.x - s0[0], b.y - s0[1], b.z - s0[2]};
+                    double D[3] = {d.x - s0[0], d.y - s0[1], d.z - s0[2]};
+                    vol6 += A[0] * (B[1] * D[2] - B[2] * D[1]) - A[1] * (B[0] * D[2] - B[2] * D[0]) +
+                            A[2] * (B[0] * D[1] - B[1] * D[0]);
+                }
+            }
+            worst = std::max(worst, fabs(fabs(vol6) / 6.0 - pc.volume(c)) / pc.volume(c));
+        }
+        EXPECT(worst < 1e-9);
+        std::vector<global_index_t> tets;
+        pc.delaunay_tetrahedra(tets);
+        EXPECT(tets.size() == sum_t);          // 4 ids per tetrahedron, each seen from its 4 cells
+        pc.save_cells("/tmp/b200geo_cells.obj", 0.1);
+        FILE* fobj = fopen("/tmp/b200geo_cells.obj", "r");
+        EXPECT(fobj != nullptr);
+        size_t nvl = 0, nfl = 0;
+        if(fobj) {
+            char line[4096];
+            while(fgets(line, sizeof(line), fobj)) {
+                nvl += line[0] == 'v';
+                nfl += line[0] == 'f';
+            }
+            fclose(fobj);
+            remove("/tmp/b200geo_cells.obj");
+        }
+        size_t sum_f = 0;
+        for(index_t c = 0; c < n; ++c) {
+            sum_f += pc.nb_v(c);
+        }
+        EXPECT(nvl == sum_t && nfl == sum_f);
+    }
     // ---- OptimalTransportMap3d: uniform target on the box, every cell reaches 1/n
     {
         OptimalTransportMap3d otm;
