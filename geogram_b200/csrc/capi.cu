@@ -386,7 +386,7 @@ void b200vor_destroy(b200vor_ctx* h) {
     cudaSetDevice(c.device);
     cudaStreamSynchronize(c.stream);
     c.xyz.release(); c.wgt.release(); c.cellid.release(); c.rank.release();
-    c.sub.release(); c.vstart.release(); c.vcount.release();
+    c.sub.release(); c.vstart.release(); c.vcount.release(); c.wloc.release(); c.wloc_tmp.release();
     c.cell_start.release(); c.perm.release(); c.scan_tmp.release(); c.sorted.release();
     c.knn.release(); c.knn_flag.release(); c.qlist.release(); c.qlist2.release(); c.qlist3.release(); c.qrows.release();
     c.counter.release(); c.m.release(); c.mg.release(); c.status.release();

@@ -41,6 +41,8 @@ struct GridDesc {
 constexpr uint32_t kDenseBin = 32;   // a uniform (Poisson, 8 per bin) input never reaches it
 constexpr uint32_t kSubPpc = 8;      // sub-grid sized for <= kSubPpc seeds per virtual cell
 constexpr int kMaxSubLog = 5;        // s <= 32
+constexpr int kWlocRingNear = 3;     // bins of dilation of the two local weight bounds (Laguerre)
+constexpr int kWlocRingFar = 8;
 
 // One seed in grid order: 32 bytes, read with two 16-byte loads.
 struct __align__(16) Seed {
@@ -123,6 +125,7 @@ struct Ctx {
     GridDesc grid;
     DevBuf<uint32_t> cellid, rank, cell_start, perm, scan_tmp;
     DevBuf<uint32_t> sub, vstart, vcount;   // two-level grid only
+    DevBuf<double> wloc, wloc_tmp;          // Laguerre only: dilated per-bin weight maxima (near | far)
     DevBuf<Seed> sorted;
 
     // kNN table of the cell pipeline (rows in pass order, ids in grid order + n*instance)

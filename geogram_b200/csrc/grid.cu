@@ -11,6 +11,9 @@
 
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
+
+#include <utility>
 
 namespace b200vor {
 
@@ -294,9 +297,91 @@ __global__ void sort_bins_kernel(uint32_t ncell, const uint32_t* __restrict__ ce
     }
 }
 
+// ---- local weight bound (Laguerre cells): wloc[b] = max weight of the seeds in the bins within
+//      Chebyshev distance kWlocRing of bin b; lets the security radius use a LOCAL weight spread
+//      (fused_kernel.inc, sr_bound) when the weights vary smoothly over the domain ----
+__global__ void bin_wmax_kernel(uint32_t ncell, const uint32_t* __restrict__ cell_start,
+                                const Seed* __restrict__ sorted, double* __restrict__ out) {
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if(b >= ncell) {
+        return;
+    }
+    double mx = -1e300;
+    for(uint32_t k = cell_start[b]; k < cell_start[b + 1]; ++k) {
+        mx = fmax(mx, sorted[k].w);
+    }
+    out[b] = mx;
+}
+
+__global__ void dilate_max_kernel(GridDesc G, int axis, int ring, const double* __restrict__ in,
+                                  double* __restrict__ out) {
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if(b >= G.ncell) {
+        return;
+    }
+    const int gx = G.g[0], gy = G.g[1];
+    int idx[3] = {int(b % uint32_t(gx)), int((b / uint32_t(gx)) % uint32_t(gy)), int(b / (uint32_t(gx) * uint32_t(gy)))};
+    const int stride[3] = {1, gx, gx * gy};
+    const int ga = G.g[axis], base = int(b) - idx[axis] * stride[axis];
+    double mx = -1e300;
+    if(2 * ring + 1 >= ga) {
+        for(int t = 0; t < ga; ++t) {
+            mx = fmax(mx, in[base + t * stride[axis]]);
+        }
+    } else {
+        for(int d = -ring; d <= ring; ++d) {
+            int t = idx[axis] + d;
+            if(t < 0 || t >= ga) {
+                if(!G.periodic) {
+                    continue;
+                }
+                t += t < 0 ? ga : -ga;
+            }
+            mx = fmax(mx, in[base + t * stride[axis]]);
+        }
+    }
+    out[b] = mx;
+}
+
 }  // namespace
 
+int build_wloc(Ctx* c) {
+    // two fields: a tight one (kWlocRingNear bins) and a wide one (kWlocRingFar bins); a cell uses
+    // the tightest whose far-field condition holds (fused_kernel.inc, sr_bound)
+    const GridDesc& G = c->grid;
+    int rc;
+    if((rc = c->wloc.reserve(2 * size_t(G.ncell))) || (rc = c->wloc_tmp.reserve(2 * size_t(G.ncell)))) {
+        return rc;
+    }
+    uint32_t nb = (G.ncell + kThreads - 1) / kThreads;
+    double* near = c->wloc.p;
+    double* far = c->wloc.p + G.ncell;
+    double* t0 = c->wloc_tmp.p;
+    double* t1 = c->wloc_tmp.p + G.ncell;
+    bin_wmax_kernel<<<nb, kThreads, 0, c->stream>>>(G.ncell, c->cell_start.p, c->sorted.p, t0);
+    dilate_max_kernel<<<nb, kThreads, 0, c->stream>>>(G, 0, kWlocRingNear, t0, t1);
+    dilate_max_kernel<<<nb, kThreads, 0, c->stream>>>(G, 1, kWlocRingNear, t1, far);
+    dilate_max_kernel<<<nb, kThreads, 0, c->stream>>>(G, 2, kWlocRingNear, far, near);
+    // the wide field is the tight one dilated further (max filters compose)
+    dilate_max_kernel<<<nb, kThreads, 0, c->stream>>>(G, 0, kWlocRingFar - kWlocRingNear, near, t0);
+    dilate_max_kernel<<<nb, kThreads, 0, c->stream>>>(G, 1, kWlocRingFar - kWlocRingNear, t0, t1);
+    dilate_max_kernel<<<nb, kThreads, 0, c->stream>>>(G, 2, kWlocRingFar - kWlocRingNear, t1, far);
+    c->stats.gpu_launches += 7;
+    B200_CUDA_CHECK(cudaGetLastError());
+    return B200VOR_OK;
+}
+
+int build_grid_impl(Ctx* c);
+
 int build_grid(Ctx* c) {
+    int rc = build_grid_impl(c);
+    if(rc == B200VOR_OK && c->has_w) {
+        rc = build_wloc(c);
+    }
+    return rc;
+}
+
+int build_grid_impl(Ctx* c) {
     const uint32_t n = c->n;
     cudaStream_t st = c->stream;
     GridDesc& G = c->grid;
