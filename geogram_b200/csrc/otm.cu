@@ -45,14 +45,18 @@ __device__ inline void instance_translation(uint32_t inst, int& tx, int& ty, int
 
 // c_if = A_if / (2 |p_i - p_j|) for every face f of every cell i, column j_f = real index of the
 // neighbour (box faces: coefficient 0); diag_i = sum_f c_if.  16 lanes per row.
+// Rows and columns are numbered in GRID order (row i = seed perm[i]; column = inv[neighbour]):
+// neighbours are then close in memory and the x[col] gathers of the SpMV stay in L1/L2.
 __global__ void otm_coef_kernel(uint32_t n, const double* __restrict__ xyz, int periodic, double period,
+                                const uint32_t* __restrict__ perm, const uint32_t* __restrict__ inv,
                                 const uint32_t* __restrict__ nfaces, const uint32_t* __restrict__ face_nbr,
                                 const double* __restrict__ face_area, uint32_t* __restrict__ col,
-                                double* __restrict__ coef, double* __restrict__ diag) {
+                                double* __restrict__ coef, double* __restrict__ diag,
+                                uint32_t* __restrict__ nfg) {
     const uint32_t lane = threadIdx.x & 15u;
     const uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
     const bool alive = row < n;
-    const uint32_t r = alive ? row : 0u;
+    const uint32_t r = alive ? perm[row] : perm[0];
     const uint32_t nf = alive ? min(nfaces[r], kFcap) : 0u;
     const double px = xyz[3 * size_t(r)], py = xyz[3 * size_t(r) + 1], pz = xyz[3 * size_t(r) + 2];
     double d = 0.0;
@@ -73,15 +77,16 @@ __global__ void otm_coef_kernel(uint32_t n, const double* __restrict__ xyz, int 
                 const double qz = xyz[3 * size_t(j) + 2] + tz * period - pz;
                 const double dist = sqrt(qx * qx + qy * qy + qz * qz);
                 cf = dist > 0.0 ? face_area[size_t(r) * kFcap + f] / (2.0 * dist) : 0.0;
+                j = inv[j];
             } else {
-                j = r;
+                j = row;
             }
         } else {
-            j = r;
+            j = row;
         }
         if(alive) {
-            col[size_t(r) * kFcap + f] = j;
-            coef[size_t(r) * kFcap + f] = cf;
+            col[size_t(row) * kFcap + f] = j;
+            coef[size_t(row) * kFcap + f] = cf;
         }
         d += cf;
     }
@@ -89,7 +94,34 @@ __global__ void otm_coef_kernel(uint32_t n, const double* __restrict__ xyz, int 
         d += __shfl_xor_sync(0xffffffffu, d, o, 16);
     }
     if(alive && lane == 0) {
-        diag[r] = d;
+        diag[row] = d;
+        nfg[row] = nf;
+    }
+}
+
+__global__ void invert_perm_kernel(uint32_t n, const uint32_t* __restrict__ perm, uint32_t* __restrict__ inv) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i < n) {
+        inv[perm[i]] = i;
+    }
+}
+
+// out[i] = in[perm[i]] (user order -> grid order)
+__global__ void gather_kernel(uint32_t n, const uint32_t* __restrict__ perm, const double* __restrict__ in,
+                              double* __restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i < n) {
+        out[i] = in[perm[i]];
+    }
+}
+
+// out[perm[i]] = a[perm[i]] + s * d[i] (d in grid order, a and out in user order)
+__global__ void axpy_scatter_kernel(uint32_t n, const uint32_t* __restrict__ perm, const double* __restrict__ a,
+                                    double s, const double* __restrict__ d, double* __restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i < n) {
+        const uint32_t r = perm[i];
+        out[r] = a[r] + s * d[i];
     }
 }
 
@@ -216,15 +248,6 @@ __global__ void otm_residual_kernel(uint32_t n, const double* __restrict__ vol, 
     }
 }
 
-// out = a + s * d ; z0 = r / diag (s == 0 form used to initialise CG)
-__global__ void axpy_out_kernel(uint32_t n, const double* __restrict__ a, double s, const double* __restrict__ d,
-                                double* __restrict__ out) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if(i < n) {
-        out[i] = a[i] + s * d[i];
-    }
-}
-
 __global__ void jacobi_kernel(uint32_t n, const double* __restrict__ r, const double* __restrict__ diag,
                               double* __restrict__ z, double* __restrict__ p) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -242,11 +265,13 @@ struct Resid {
 
 struct Work {
     DevBuf<double> nu, b, x, r, z, p, q, diag, coef, w0, w1, part;
-    DevBuf<uint32_t> col;
+    DevBuf<uint32_t> col, inv, nfg;
+    DevBuf<double> bg;
     ~Work() { release(); }
     void release() {
         nu.release(); b.release(); x.release(); r.release(); z.release(); p.release(); q.release();
         diag.release(); coef.release(); w0.release(); w1.release(); part.release(); col.release();
+        inv.release(); nfg.release(); bg.release();
     }
 };
 
@@ -371,7 +396,8 @@ int otm_newton(Ctx* c, const double* nu_in, double* w_io, const b200vor_otm_para
     if((rc = W.b.reserve(n)) || (rc = W.x.reserve(n)) || (rc = W.r.reserve(n)) || (rc = W.z.reserve(n)) ||
        (rc = W.p.reserve(n)) || (rc = W.q.reserve(n)) || (rc = W.diag.reserve(n)) || (rc = W.w0.reserve(n)) ||
        (rc = W.w1.reserve(n)) || (rc = W.part.reserve(4 * kNB)) || (rc = W.coef.reserve(size_t(n) * kFcap)) ||
-       (rc = W.col.reserve(size_t(n) * kFcap))) {
+       (rc = W.col.reserve(size_t(n) * kFcap)) || (rc = W.inv.reserve(n)) || (rc = W.nfg.reserve(n)) ||
+       (rc = W.bg.reserve(n))) {
         return fail(rc);
     }
     cudaStream_t st = c->stream;
@@ -435,12 +461,15 @@ int otm_newton(Ctx* c, const double* nu_in, double* w_io, const b200vor_otm_para
     uint32_t it = 0;
     for(; it < P.max_newton && cur.maxrel > P.epsilon; ++it) {
         // ---- Hessian of this iterate from the face lists ----
-        otm_coef_kernel<<<rblk, kNT, 0, st>>>(n, c->xyz.p, c->periodic, c->period, c->nfaces.p, c->face_nbr.p,
-                                              c->face_area.p, W.col.p, W.coef.p, W.diag.p);
-        c->stats.gpu_launches++;
-        // ---- L delta = nu - vol by Jacobi-preconditioned CG, delta_0 = 0 ----
+        // (the grid order depends on the points only: identical for every weight vector)
+        invert_perm_kernel<<<nblk, kNT, 0, st>>>(n, c->perm.p, W.inv.p);
+        otm_coef_kernel<<<rblk, kNT, 0, st>>>(n, c->xyz.p, c->periodic, c->period, c->perm.p, W.inv.p, c->nfaces.p,
+                                              c->face_nbr.p, c->face_area.p, W.col.p, W.coef.p, W.diag.p, W.nfg.p);
+        c->stats.gpu_launches += 2;
+        // ---- L delta = nu - vol by Jacobi-preconditioned CG in grid order, delta_0 = 0 ----
         B200_CUDA_CHECK(cudaMemsetAsync(W.x.p, 0, size_t(n) * sizeof(double), st));
-        B200_CUDA_CHECK(cudaMemcpyAsync(W.r.p, W.b.p, size_t(n) * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        gather_kernel<<<nblk, kNT, 0, st>>>(n, c->perm.p, W.b.p, W.r.p);
+        c->stats.gpu_launches++;
         jacobi_kernel<<<nblk, kNT, 0, st>>>(n, W.r.p, W.diag.p, W.z.p, W.p.p);
         c->stats.gpu_launches++;
         double rz = 0.0, bb = 0.0;
@@ -451,7 +480,7 @@ int otm_newton(Ctx* c, const double* nu_in, double* w_io, const b200vor_otm_para
         double rr = bb;
         uint32_t k = 0;
         for(; k < P.max_cg && rr > stop2; ++k) {
-            otm_spmv_kernel<<<rblk, kNT, 0, st>>>(n, c->nfaces.p, W.col.p, W.coef.p, W.p.p, W.q.p);
+            otm_spmv_kernel<<<rblk, kNT, 0, st>>>(n, W.nfg.p, W.col.p, W.coef.p, W.p.p, W.q.p);
             c->stats.gpu_launches++;
             double pq = 0.0;
             if((rc = dot(c, W, W.p.p, W.q.p, &pq))) {
@@ -484,7 +513,7 @@ int otm_newton(Ctx* c, const double* nu_in, double* w_io, const b200vor_otm_para
         Resid trial = cur;
         bool accepted = false;
         for(int halv = 0; halv < 40; ++halv) {
-            axpy_out_kernel<<<nblk, kNT, 0, st>>>(n, W.w0.p, alpha, W.x.p, W.w1.p);
+            axpy_scatter_kernel<<<nblk, kNT, 0, st>>>(n, c->perm.p, W.w0.p, alpha, W.x.p, W.w1.p);
             c->stats.gpu_launches++;
             if((rc = vec_max(c, W, W.w1.p, &wmax)) || (rc = eval_cells(c, W.w1.p, wmax))) {
                 return fail(rc);
