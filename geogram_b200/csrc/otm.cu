@@ -21,6 +21,7 @@
 #include <math.h>
 #include <string.h>
 
+#include <algorithm>
 #include <vector>
 
 namespace b200vor {
@@ -177,10 +178,16 @@ __global__ void dot_kernel(uint32_t n, const double* __restrict__ a, const doubl
     }
 }
 
+// The CG scalars live on the device (no host round trip per iteration):
+// sc[0] = r.z, sc[1] = alpha, sc[2] = beta, sc[3] = r.r, sc[4] = stop threshold on r.r,
+// sc[5] = 1 once converged (or the direction fell into the null space), sc[6] = iterations applied
+enum { kRZ = 0, kAlpha, kBeta, kRR, kStop, kDone, kIters, kNScalars };
+
 // x += alpha p ; r -= alpha q ; z = r / diag ; partials of r.z and r.r
-__global__ void cg_update_kernel(uint32_t n, double alpha, const double* __restrict__ p, const double* __restrict__ q,
-                                 const double* __restrict__ diag, double* __restrict__ x, double* __restrict__ r,
-                                 double* __restrict__ z, double* __restrict__ part) {
+__global__ void cg_update_kernel(uint32_t n, const double* __restrict__ sc, const double* __restrict__ p,
+                                 const double* __restrict__ q, const double* __restrict__ diag, double* __restrict__ x,
+                                 double* __restrict__ r, double* __restrict__ z, double* __restrict__ part) {
+    const double alpha = sc[kAlpha];
     const uint32_t per = (n + gridDim.x - 1) / gridDim.x;
     const uint32_t lo = blockIdx.x * per, hi = min(n, lo + per);
     double rz = 0.0, rr = 0.0;
@@ -202,11 +209,38 @@ __global__ void cg_update_kernel(uint32_t n, double alpha, const double* __restr
     }
 }
 
+// alpha = r.z / p.q from the ordered sum of the partials of p.q
+__global__ void cg_alpha_kernel(const double* __restrict__ part, double* __restrict__ sc) {
+    double pq = 0.0;
+    for(int b = 0; b < kNB; ++b) {
+        pq += part[b];
+    }
+    const bool stop = sc[kDone] != 0.0 || !(sc[kRR] > sc[kStop]) || !(pq > 0.0);
+    sc[kDone] = stop ? 1.0 : 0.0;
+    sc[kAlpha] = stop ? 0.0 : sc[kRZ] / pq;
+}
+
+// beta = (r.z)_new / (r.z)_old from the ordered sums of the partials of the update kernel
+__global__ void cg_beta_kernel(const double* __restrict__ part, double* __restrict__ sc) {
+    double rz_new = 0.0, rr = 0.0;
+    for(int b = 0; b < kNB; ++b) {
+        rz_new += part[b];
+        rr += part[kNB + b];
+    }
+    if(sc[kDone] == 0.0) {
+        sc[kBeta] = rz_new / sc[kRZ];
+        sc[kRZ] = rz_new;
+        sc[kRR] = rr;
+        sc[kIters] += 1.0;
+    }
+}
+
 // p = z + beta p
-__global__ void cg_dir_kernel(uint32_t n, double beta, const double* __restrict__ z, double* __restrict__ p) {
+__global__ void cg_dir_kernel(uint32_t n, const double* __restrict__ sc, const double* __restrict__ z,
+                              double* __restrict__ p) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if(i < n) {
-        p[i] = z[i] + beta * p[i];
+    if(i < n && sc[kDone] == 0.0) {
+        p[i] = z[i] + sc[kBeta] * p[i];
     }
 }
 
@@ -395,7 +429,7 @@ int otm_newton(Ctx* c, const double* nu_in, double* w_io, const b200vor_otm_para
     auto fail = [&](int code) { return code; };   // W releases its buffers when it goes out of scope
     if((rc = W.b.reserve(n)) || (rc = W.x.reserve(n)) || (rc = W.r.reserve(n)) || (rc = W.z.reserve(n)) ||
        (rc = W.p.reserve(n)) || (rc = W.q.reserve(n)) || (rc = W.diag.reserve(n)) || (rc = W.w0.reserve(n)) ||
-       (rc = W.w1.reserve(n)) || (rc = W.part.reserve(4 * kNB)) || (rc = W.coef.reserve(size_t(n) * kFcap)) ||
+       (rc = W.w1.reserve(n)) || (rc = W.part.reserve(4 * kNB + 16)) || (rc = W.coef.reserve(size_t(n) * kFcap)) ||
        (rc = W.col.reserve(size_t(n) * kFcap)) || (rc = W.inv.reserve(n)) || (rc = W.nfg.reserve(n)) ||
        (rc = W.bg.reserve(n))) {
         return fail(rc);
@@ -476,36 +510,29 @@ int otm_newton(Ctx* c, const double* nu_in, double* w_io, const b200vor_otm_para
         if((rc = dot(c, W, W.r.p, W.z.p, &rz)) || (rc = dot(c, W, W.r.p, W.r.p, &bb))) {
             return fail(rc);
         }
-        const double stop2 = P.cg_tol * P.cg_tol * bb;
-        double rr = bb;
+        // device-resident scalars; the host looks at them every 16 iterations only
+        double hsc[kNScalars] = {rz, 0.0, 0.0, bb, P.cg_tol * P.cg_tol * bb, 0.0, 0.0};
+        double* sc = W.part.p + 4 * kNB;
+        B200_CUDA_CHECK(cudaMemcpyAsync(sc, hsc, sizeof(hsc), cudaMemcpyHostToDevice, st));
         uint32_t k = 0;
-        for(; k < P.max_cg && rr > stop2; ++k) {
-            otm_spmv_kernel<<<rblk, kNT, 0, st>>>(n, W.nfg.p, W.col.p, W.coef.p, W.p.p, W.q.p);
-            c->stats.gpu_launches++;
-            double pq = 0.0;
-            if((rc = dot(c, W, W.p.p, W.q.p, &pq))) {
-                return fail(rc);
+        for(uint32_t launched = 0; launched < P.max_cg;) {
+            const uint32_t burst = std::min<uint32_t>(16u, P.max_cg - launched);
+            for(uint32_t t = 0; t < burst; ++t) {
+                otm_spmv_kernel<<<rblk, kNT, 0, st>>>(n, W.nfg.p, W.col.p, W.coef.p, W.p.p, W.q.p);
+                dot_kernel<<<kNB, kNT, 0, st>>>(n, W.p.p, W.q.p, W.part.p);
+                cg_alpha_kernel<<<1, 1, 0, st>>>(W.part.p, sc);
+                cg_update_kernel<<<kNB, kNT, 0, st>>>(n, sc, W.p.p, W.q.p, W.diag.p, W.x.p, W.r.p, W.z.p, W.part.p);
+                cg_beta_kernel<<<1, 1, 0, st>>>(W.part.p, sc);
+                cg_dir_kernel<<<nblk, kNT, 0, st>>>(n, sc, W.z.p, W.p.p);
             }
-            if(!(pq > 0.0)) {
-                break;   // direction in the null space (constants): the system is solved
+            c->stats.gpu_launches += 6ull * burst;
+            launched += burst;
+            B200_CUDA_CHECK(cudaMemcpyAsync(hsc, sc, sizeof(hsc), cudaMemcpyDeviceToHost, st));
+            B200_CUDA_CHECK(cudaStreamSynchronize(st));
+            k = uint32_t(hsc[kIters]);
+            if(hsc[kDone] != 0.0 || !(hsc[kRR] > hsc[kStop])) {
+                break;
             }
-            const double alpha = rz / pq;
-            cg_update_kernel<<<kNB, kNT, 0, st>>>(n, alpha, W.p.p, W.q.p, W.diag.p, W.x.p, W.r.p, W.z.p, W.part.p);
-            c->stats.gpu_launches++;
-            double h[2 * kNB];
-            if((rc = host_sum(c, W.part.p, 2 * kNB, h))) {
-                return fail(rc);
-            }
-            double rz_new = 0.0;
-            rr = 0.0;
-            for(int b = 0; b < kNB; ++b) {
-                rz_new += h[b];
-                rr += h[kNB + b];
-            }
-            const double beta = rz_new / rz;
-            rz = rz_new;
-            cg_dir_kernel<<<nblk, kNT, 0, st>>>(n, beta, W.z.p, W.p.p);
-            c->stats.gpu_launches++;
         }
         R.cg_iters += k;
         // ---- KMT damping ----
