@@ -41,6 +41,7 @@ struct GridDesc {
 constexpr uint32_t kDenseBin = 32;   // a uniform (Poisson, 8 per bin) input never reaches it
 constexpr uint32_t kSubPpc = 8;      // sub-grid sized for <= kSubPpc seeds per virtual cell
 constexpr int kMaxSubLog = 5;        // s <= 32
+constexpr int kSmallPeriodicGrid = 12; // periodic grids with fewer bins per axis take the two-level walk
 constexpr int kWlocRingNear = 3;     // bins of dilation of the two local weight bounds (Laguerre)
 constexpr int kWlocRingFar = 8;
 

@@ -13,6 +13,7 @@
 #include <stdarg.h>
 #include <stdlib.h>
 
+#include <algorithm>
 #include <utility>
 
 namespace b200vor {
@@ -473,6 +474,12 @@ int build_grid_impl(Ctx* c) {
     uint32_t dense = 0;
     B200_CUDA_CHECK(cudaMemcpyAsync(&dense, dense_flag, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     B200_CUDA_CHECK(cudaStreamSynchronize(st));
+    // small periodic grids also take the two-level walk (with 1x1x1 sub-grids): it enumerates the
+    // bins of its box one by one, each with its own periodic image, so the box may span up to
+    // three periods -- what a cell reaching beyond half a period needs (27 instances)
+    if(c->periodic && std::min(G.g[0], std::min(G.g[1], G.g[2])) < kSmallPeriodicGrid) {
+        dense = 1;
+    }
     G.two_level = dense ? 1 : 0;
     G.nvirt = G.ncell;
     if(!dense) {
