@@ -27,7 +27,7 @@ EXPORTS = [
     "b200vor_version", "b200vor_last_error", "b200vor_create", "b200vor_destroy",
     "b200vor_set_domain_box", "b200vor_set_domain_periodic", "b200vor_set_points",
     "b200vor_knn", "b200vor_knn_points", "b200vor_compute_cells", "b200vor_get_cells",
-    "b200vor_get_faces", "b200vor_get_vertices", "b200vor_get_cvt", "b200vor_otm_newton", "b200vor_lloyd", "b200vor_get_stats",
+    "b200vor_get_faces", "b200vor_get_vertices", "b200vor_get_cvt", "b200vor_otm_newton", "b200vor_get_spatial_order", "b200vor_lloyd", "b200vor_get_stats",
     "b200vor_set_points_per_cell", "b200vor_set_stream", "b200vor_set_query_range",
 ]
 
@@ -114,6 +114,7 @@ def load_library():
     lib.b200vor_get_vertices.argtypes = [vp, vp, vp, vp, u32, i32]
     lib.b200vor_get_cvt.argtypes = [vp, vp, vp, ctypes.POINTER(dbl), i32]
     lib.b200vor_otm_newton.argtypes = [vp, vp, vp, ctypes.POINTER(OtmParams), ctypes.POINTER(OtmResult), i32]
+    lib.b200vor_get_spatial_order.argtypes = [vp, vp, i32]
     lib.b200vor_lloyd.argtypes = [vp, u32, ctypes.POINTER(CellParams), vp, i32]
     lib.b200vor_get_stats.argtypes = [vp, ctypes.POINTER(Stats)]
     lib.b200vor_set_points_per_cell.argtypes = [vp, dbl]
@@ -241,6 +242,12 @@ class Context(object):
         self._check(self.lib.b200vor_get_vertices(self.h, _ptr(nv), _ptr(xyz), _ptr(vf), FCAP, 0))
         faces = np.stack([vf & 0xFF, (vf >> 8) & 0xFF, (vf >> 16) & 0xFF], axis=-1).astype(np.uint8)
         return nv, xyz, faces
+
+    def spatial_order(self):
+        """permutation of the seeds in grid order (spatial sort; role of compute_Hilbert_order)"""
+        order = np.zeros(self.n, np.uint32)
+        self._check(self.lib.b200vor_get_spatial_order(self.h, _ptr(order), 0))
+        return order
 
     def get_cvt(self):
         """(f_total, f_cell[n], g[n,3]) of the CVT objective (RVD.cpp:791-876); needs

@@ -810,6 +810,24 @@ int b200vor_lloyd(b200vor_ctx* h, uint32_t iters, const b200vor_cell_params* par
     return B200VOR_OK;
 }
 
+int b200vor_get_spatial_order(b200vor_ctx* h, uint32_t* order, int on_device) {
+    if(!h || !order || h->c.n == 0) {
+        set_error("b200vor_get_spatial_order: needs a context with points and an output array");
+        return B200VOR_ERR_ARG;
+    }
+    Ctx* c = &h->c;
+    B200_CUDA_CHECK(cudaSetDevice(c->device));
+    int rc;
+    if(c->grid_dirty && (rc = ensure_grid(c))) {
+        return rc;
+    }
+    if((rc = copy_out(order, c->perm.p, size_t(c->n) * sizeof(uint32_t), on_device, c->stream))) {
+        return rc;
+    }
+    B200_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return B200VOR_OK;
+}
+
 int b200vor_get_stats(b200vor_ctx* h, b200vor_stats* stats) {
     if(!h || !stats) {
         set_error("b200vor_get_stats: null argument");

@@ -442,6 +442,100 @@ void CentroidalVoronoiTesselation::funcgrad(index_t n, double* x, double& f, dou
     }
 }
 
+void CentroidalVoronoiTesselation::Newton_iterations(index_t nb_iter, index_t m) {
+    const size_t N = points_.size();
+    if(N == 0 || nb_iter == 0) {
+        return;
+    }
+    m = std::max<index_t>(m, 1);
+    std::vector<double> x(points_), g(N), xn(N), gn(N), d(N);
+    std::vector<std::vector<double> > S, Y;
+    std::vector<double> rho;
+    double f = 0.0;
+    funcgrad(index_t(N), x.data(), f, g.data());
+    auto dot = [&](const std::vector<double>& a, const std::vector<double>& b) {
+        double s = 0.0;
+        for(size_t k = 0; k < N; ++k) {
+            s += a[k] * b[k];
+        }
+        return s;
+    };
+    for(index_t it = 0; it < nb_iter; ++it) {
+        // two-loop recursion: d = -H g
+        d = g;
+        std::vector<double> al(S.size());
+        for(size_t k = S.size(); k-- > 0;) {
+            al[k] = rho[k] * dot(S[k], d);
+            for(size_t j = 0; j < N; ++j) {
+                d[j] -= al[k] * Y[k][j];
+            }
+        }
+        if(!S.empty()) {
+            const double gamma = dot(S.back(), Y.back()) / dot(Y.back(), Y.back());
+            for(size_t j = 0; j < N; ++j) {
+                d[j] *= gamma;
+            }
+        } else {
+            // first step: the Lloyd step x - g / (2 m_i) is exact for fixed cells; 1/(2 <m>) per point
+            const double scale = double(nb_points()) / 2.0;
+            for(size_t j = 0; j < N; ++j) {
+                d[j] *= scale;
+            }
+        }
+        for(size_t k = 0; k < S.size(); ++k) {
+            const double be = rho[k] * dot(Y[k], d);
+            for(size_t j = 0; j < N; ++j) {
+                d[j] += (al[k] - be) * S[k][j];
+            }
+        }
+        for(size_t j = 0; j < N; ++j) {
+            d[j] = -d[j];
+        }
+        double gd = dot(g, d);
+        if(!(gd < 0.0)) {   // not a descent direction: restart from steepest descent
+            S.clear(); Y.clear(); rho.clear();
+            for(size_t j = 0; j < N; ++j) {
+                d[j] = -g[j] * double(nb_points()) / 2.0;
+            }
+            gd = dot(g, d);
+        }
+        // Armijo backtracking
+        double t = 1.0, fn = f;
+        bool ok = false;
+        for(int ls = 0; ls < 20; ++ls) {
+            for(size_t j = 0; j < N; ++j) {
+                xn[j] = x[j] + t * d[j];
+            }
+            funcgrad(index_t(N), xn.data(), fn, gn.data());
+            if(fn <= f + 1e-4 * t * gd) {
+                ok = true;
+                break;
+            }
+            t *= 0.5;
+        }
+        if(!ok) {
+            break;
+        }
+        std::vector<double> s(N), y(N);
+        for(size_t j = 0; j < N; ++j) {
+            s[j] = xn[j] - x[j];
+            y[j] = gn[j] - g[j];
+        }
+        const double sy = dot(s, y);
+        if(sy > 1e-300) {
+            if(S.size() == m) {
+                S.erase(S.begin()); Y.erase(Y.begin()); rho.erase(rho.begin());
+            }
+            S.push_back(s); Y.push_back(y); rho.push_back(1.0 / sy);
+        }
+        x.swap(xn);
+        g.swap(gn);
+        f = fn;
+    }
+    points_ = x;
+    last_f_ = f;
+}
+
 void CentroidalVoronoiTesselation::Lloyd_iterations(index_t nb_iter) {
     const index_t n = nb_points();
     if(n == 0 || nb_iter == 0) {

@@ -192,11 +192,19 @@ public:
        (ComputeCVTFuncGradVolumetric, RVD.cpp:791-876); locked points get g = 0
        (constrain_points, CVT.cpp:309-321).  Security-radius checking is always on. */
     void funcgrad(index_t n, double* x, double& f, double* g);
+    /* quasi-Newton minimisation of the CVT energy (CVT.cpp:272-307): L-BFGS with m correction pairs
+       on the host, every objective evaluation = one funcgrad() on the device.  The reference hands
+       funcgrad to HLBFGS (third party); this is the textbook two-loop recursion with Armijo
+       backtracking, so iterates differ from HLBFGS while the fixed points are the same. */
+    void Newton_iterations(index_t nb_iter, index_t m = 7);
+    /* energy of the current points (last funcgrad evaluation of Newton_iterations) */
+    double last_energy() const { return last_f_; }
 
 private:
     b200vor_ctx* ctx_;
     std::vector<double> points_;
     std::vector<bool> point_is_locked_;
+    double last_f_ = 0.0;
 };
 
 /* Semi-discrete optimal transport between the uniform measure of the domain (unit cube, a box or

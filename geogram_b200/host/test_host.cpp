@@ -180,6 +180,23 @@ int main() {
         cvt.funcgrad(3 * n, x2.data(), f2, g2.data());
         EXPECT(fabs((f0 - f2) / h - gg) < 0.05 * gg);
     }
+    // ---- Newton_iterations (L-BFGS on the device objective): lower energy than the same number of
+    //      Lloyd iterations from the same start
+    {
+        CentroidalVoronoiTesselation a(3), b(3);
+        a.set_points(n, pts.data());
+        b.set_points(n, pts.data());
+        a.Lloyd_iterations(8);
+        b.Newton_iterations(8);
+        std::vector<double> xa(a.embedding(0), a.embedding(0) + 3 * size_t(n)), ga(3 * size_t(n));
+        double fa = 0, f0 = 0;
+        a.funcgrad(3 * n, xa.data(), fa, ga.data());
+        std::vector<double> x0(pts);
+        a.funcgrad(3 * n, x0.data(), f0, ga.data());
+        printf("CVT energy: start %.6e  8 Lloyd %.6e  8 Newton (L-BFGS) %.6e\n", f0, fa, b.last_energy());
+        EXPECT(b.last_energy() < f0 * 0.9);
+        EXPECT(b.last_energy() <= fa * 1.02);
+    }
     // ---- cell geometry export: loops close, volume from the exported geometry, tetrahedra, OBJ
     {
         ConvexCellBatch pc;

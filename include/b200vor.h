@@ -33,6 +33,7 @@
  *   b200vor_get_cvt          ComputeCVTFuncGradVolumetric (f, g)    voronoi/RVD.cpp:791-876
  *   b200vor_otm_newton       [external] OptimalTransportMap3d::optimize (exploragram; call sites
  *                            src/examples/exploragram/compute_OTM/main.cpp:284-297)
+ *   b200vor_get_spatial_order  compute_Hilbert_order (role)         mesh/mesh_reorder.cpp:1260-1300
  *   b200vor_lloyd            CentroidalVoronoiTesselation::Lloyd_iterations
  *                                                                   voronoi/CVT.cpp:133-169
  */
@@ -196,6 +197,13 @@ int b200vor_set_stream(b200vor_ctx* ctx, void* cuda_stream);
 /* multi-GPU sharding: compute (and Lloyd-update) only the cells of the seeds whose index
  * lies in [first, last); every rank still holds all seeds (default: all) */
 int b200vor_set_query_range(b200vor_ctx* ctx, uint32_t first, uint32_t last);
+
+/* ---- spatial order ---- */
+/* order[n]: the seeds in the order of the counting-sort grid (bin by bin, x fastest; inside a bin by
+ * index) -- a spatial sort of the point set in the role of the reference's Hilbert / BRIO
+ * pre-ordering (mesh/mesh_reorder.cpp:1260-1300, compute_Hilbert_order): consecutive entries are
+ * neighbours in space.  Available after b200vor_set_points. */
+int b200vor_get_spatial_order(b200vor_ctx* ctx, uint32_t* order, int on_device);
 
 /* ---- introspection ---- */
 int b200vor_get_stats(b200vor_ctx* ctx, b200vor_stats* stats);

@@ -457,6 +457,20 @@ def test_edge_cases(Context, port):
         Context(0).compute_cells()
 
 
+def test_spatial_order(Context):
+    """grid order: a permutation whose consecutive entries are close in space"""
+    n = 100000
+    xyz = oracles.uniform_seeds(n, 8)
+    ctx = Context(0)
+    ctx.set_points(xyz)
+    order = ctx.spatial_order()
+    assert sorted(order.tolist()) == list(range(n))
+    step = np.linalg.norm(np.diff(xyz[order], axis=0), axis=1)
+    rand = np.linalg.norm(np.diff(xyz, axis=0), axis=1)
+    assert np.median(step) < 0.1 * np.median(rand)
+    ctx.close()
+
+
 def test_fuzz_small_and_odd_inputs(Context, port):
     """Small, skewed and shifted inputs against the oracle port: tiny n (grid of one bin), flat and
     elongated clipping boxes, large coordinate offsets, tight pairs, weights.  A cell the GPU

@@ -29,6 +29,9 @@ def test_host_library_exports_the_mirrored_interfaces():
         "B200GEO::ConvexCellBatch::compute_mg(",
         "B200GEO::CentroidalVoronoiTesselation::Lloyd_iterations(unsigned int)",
         "B200GEO::CentroidalVoronoiTesselation::funcgrad(unsigned int, double*, double&, double*)",
+        "B200GEO::CentroidalVoronoiTesselation::Newton_iterations(unsigned int, unsigned int)",
+        "B200GEO::ConvexCellBatch::save_cells(",
+        "B200GEO::ConvexCellBatch::delaunay_tetrahedra(",
         "B200GEO::OptimalTransportMap3d::set_points(unsigned int, double const*)",
         "B200GEO::OptimalTransportMap3d::optimize(unsigned int)",
     ]:
