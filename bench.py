@@ -150,6 +150,12 @@ def main():
         run_reference(args, rank)
         return
 
+    # stdout carries exactly ONE JSON line: libraries that chat on stdout (NCCL prints its version
+    # there) are sent to stderr for the duration of the run
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
     import numpy as np
     import torch
     from geogram_b200 import Context
@@ -342,7 +348,8 @@ def main():
                 "note": "whole job: every rank moves its own rows (24 B/seed each way)"},
         "gpu_launches": int(launches), "clocks": clocks,
     }
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
