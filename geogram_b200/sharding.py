@@ -87,6 +87,7 @@ class ShardedLloyd(object):
             ctx.set_query_range(self.first, self.last)
         self.phase = {"ms_grid": 0.0, "ms_knn": 0.0, "ms_clip": 0.0}
         self._comm = []
+        self._stale = False     # sharded: the context still holds the seeds of the previous step
 
     # ---- seeds in ----
     def set_seeds_device(self, full, slabs=False):
@@ -100,6 +101,7 @@ class ShardedLloyd(object):
         else:
             self.full.copy_(full)
         self.ctx.set_points_device(self.n_total, self.full.data_ptr())
+        self._stale = False
         self._take("ms_grid")
 
     def set_shard_host(self, host_rows):
@@ -110,7 +112,16 @@ class ShardedLloyd(object):
         if self.world > 1:
             self._gather(mine)
         self.ctx.set_points_device(self.n_total, self.full.data_ptr())
+        self._stale = False
         self._take("ms_grid")
+
+    def _refresh(self):
+        """Grid of the all-gathered seeds, built when the next step needs it (a caller that
+        uploads new seeds every step never pays for the rebuild after the step)."""
+        if self._stale:
+            self.ctx.set_points_device(self.n_total, self.full.data_ptr())
+            self._stale = False
+            self._take("ms_grid")
 
     # ---- one Lloyd iteration ----
     def step(self, k0=0, mode=0):
@@ -118,11 +129,11 @@ class ShardedLloyd(object):
             self.ctx.lloyd_device(1, None, k0=k0, mode=mode)    # seeds stay resident, updated in place
             self._take("ms_grid", "ms_knn", "ms_clip")
             return
+        self._refresh()
         self.ctx.lloyd_device(1, self.out.data_ptr(), k0=k0, mode=mode)
         self._take("ms_knn", "ms_clip")
         self._gather(self.out[self.first:self.last])
-        self.ctx.set_points_device(self.n_total, self.full.data_ptr())   # grid rebuild on the new seeds
-        self._take("ms_grid")
+        self._stale = True          # the grid of the new seeds is built lazily (_refresh)
 
     def get_shard_host(self, host_rows):
         """Own rows of the current seeds -> host tensor (D2H of the own rows only)."""

@@ -166,5 +166,7 @@ def test_sharded_lloyd_gloo(world, n_total):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert err < 1e-14
-    assert calls == ["set_points"] + ["lloyd", "set_points"] * 3
-    assert phase["ms_clip"] == 6.0 and phase["ms_grid"] == 4.0
+    # the grid of the re-gathered seeds is built lazily, by the step that needs it: no rebuild
+    # after the last step (a caller that uploads fresh seeds every step pays for one build, not two)
+    assert calls == ["set_points", "lloyd"] + ["set_points", "lloyd"] * 2
+    assert phase["ms_clip"] == 6.0 and phase["ms_grid"] == 3.0
