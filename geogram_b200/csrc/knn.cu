@@ -27,6 +27,8 @@ struct KnnParams {
     GridDesc G;
     const Seed* sorted;
     const uint32_t* cell_start;
+    const uint32_t* sub;      // two-level grid (grid.cu): per-bin sub-grid word, virtual start table
+    const uint32_t* vstart;
     const uint32_t* perm;
     uint32_t n;
     KnnJob job;
@@ -158,6 +160,111 @@ __device__ inline void scan_row(const KnnParams& P, Heap<kStride>& H, int xa, in
     }
 }
 
+// Two-level grid (clustered seeds, non-periodic): the search box grows in the FINE units of the
+// query's own bin (1, 2, 4, ... sub-cells around it); every round scans the sub-cells the box meets
+// and offers the seeds that lie inside the box but were outside the previous one, so that each seed
+// is offered exactly once whatever the resolutions of the bins involved.  Complete when the k-th
+// distance is smaller than the distance to the faces of the box.
+template <int kStride>
+__device__ inline bool search_two_level(const KnnParams& P, Heap<kStride>& H, double qx, double qy, double qz,
+                                        uint32_t want) {
+    const GridDesc& G = P.G;
+    int cc[3];
+    cell_coords(G, qx, qy, qz, cc[0], cc[1], cc[2]);
+    const double q[3] = {qx, qy, qz};
+    const uint32_t hb = uint32_t(cc[0]) + uint32_t(G.g[0]) * (uint32_t(cc[1]) + uint32_t(G.g[1]) * uint32_t(cc[2]));
+    const int ls0 = int(__ldg(P.sub + hb) & 7u), s0 = 1 << ls0;
+    int f0[3];
+    double wl[3];
+    for(int a = 0; a < 3; ++a) {
+        f0[a] = cc[a] * s0 + clampi(int(floor((q[a] - G.lo[a]) * (G.inv_w[a] * double(s0)))) - cc[a] * s0, 0, s0 - 1);
+        wl[a] = G.w[a] / double(s0);
+    }
+    double plo[3] = {1e300, 1e300, 1e300}, phi[3] = {-1e300, -1e300, -1e300};   // previous box (empty)
+    for(int r = 1;; r *= 2) {
+        double blo[3], bhi[3];
+        int bl[3], bh[3];
+        bool covers_all = true;
+        for(int a = 0; a < 3; ++a) {
+            const int fl = f0[a] - r, fh = f0[a] + r;
+            // a box face beyond the grid is at infinity: nothing lies behind it
+            // (the membership box is shrunk by eps: a seed closer than eps to a face waits for the
+            //  next round, so that rounding in the stored sub-cell index can never hide a seed
+            //  that the coordinate test places inside)
+            const double eps = 1e-9 * G.w[a];
+            blo[a] = fl <= 0 ? -1e300 : G.lo[a] + fl * wl[a] + eps;
+            bhi[a] = fh >= (G.g[a] << ls0) - 1 ? 1e300 : G.lo[a] + (fh + 1) * wl[a] - eps;
+            covers_all = covers_all && blo[a] <= -1e300 && bhi[a] >= 1e300;
+            bl[a] = max(fl >> ls0, 0);
+            bh[a] = min(fh >> ls0, G.g[a] - 1);
+        }
+        for(int bz = bl[2]; bz <= bh[2]; ++bz) {
+            for(int by = bl[1]; by <= bh[1]; ++by) {
+                for(int bx = bl[0]; bx <= bh[0]; ++bx) {
+                    const uint32_t b = uint32_t(bx) + uint32_t(G.g[0]) * (uint32_t(by) + uint32_t(G.g[1]) * uint32_t(bz));
+                    if(__ldg(P.cell_start + b + 1) == __ldg(P.cell_start + b)) {
+                        continue;
+                    }
+                    const uint32_t sw = __ldg(P.sub + b);
+                    const int ls = int(sw & 7u), sd = 1 << ls;
+                    const int bi[3] = {bx, by, bz};
+                    int ra[3], rb[3];
+                    for(int a = 0; a < 3; ++a) {
+                        int lof, hif;
+                        if(ls >= ls0) {
+                            lof = (f0[a] - r) * (1 << (ls - ls0));
+                            hif = (f0[a] + r + 1) * (1 << (ls - ls0)) - 1;
+                        } else {
+                            lof = (f0[a] - r) >> (ls0 - ls);
+                            hif = (f0[a] + r) >> (ls0 - ls);
+                        }
+                        const int base = bi[a] * sd;
+                        ra[a] = max(lof, base) - base;
+                        rb[a] = min(hif, base + sd - 1) - base;
+                    }
+                    for(int z = ra[2]; z <= rb[2]; ++z) {
+                        for(int y = ra[1]; y <= rb[1]; ++y) {
+                            const uint32_t vb = (sw >> 3) + uint32_t(sd) * (uint32_t(y) + uint32_t(sd) * uint32_t(z));
+                            const uint32_t ja = __ldg(P.vstart + vb + uint32_t(ra[0]));
+                            const uint32_t jb = __ldg(P.vstart + vb + uint32_t(rb[0]) + 1u);
+                            for(uint32_t j = ja; j < jb; ++j) {
+                                Seed sj = load_seed(P.sorted + j);
+                                const bool in_new = sj.x >= blo[0] && sj.x < bhi[0] && sj.y >= blo[1] && sj.y < bhi[1] &&
+                                                    sj.z >= blo[2] && sj.z < bhi[2];
+                                const bool in_old = sj.x >= plo[0] && sj.x < phi[0] && sj.y >= plo[1] && sj.y < phi[1] &&
+                                                    sj.z >= plo[2] && sj.z < phi[2];
+                                if(in_new && !in_old) {
+                                    double dx = __dsub_rn(sj.x, qx), dy = __dsub_rn(sj.y, qy), dz = __dsub_rn(sj.z, qz);
+                                    double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                                    H.offer(d2, j);
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        if(covers_all) {
+            return true;    // every seed was offered
+        }
+        double dmin = 1e300;
+        for(int a = 0; a < 3; ++a) {
+            dmin = fmin(dmin, fmin(q[a] - blo[a], bhi[a] - q[a]));
+        }
+        dmin -= 1e-9 * G.w[0];
+        if(H.count >= want && dmin > 0.0 && H.d[0] < dmin * dmin) {
+            return true;
+        }
+        for(int a = 0; a < 3; ++a) {
+            plo[a] = blo[a];
+            phi[a] = bhi[a];
+        }
+        if(r > (1 << 30) / 2) {
+            return false;
+        }
+    }
+}
+
 template <int kBlock>
 __global__ void __launch_bounds__(kBlock) knn_kernel(KnnParams P) {
     constexpr int kStride = kBlock + 1;
@@ -197,6 +304,10 @@ __global__ void __launch_bounds__(kBlock) knn_kernel(KnnParams P) {
         }
         int cx, cy, cz;
         cell_coords(G, qx, qy, qz, cx, cy, cz);
+        const bool two_level = G.two_level && !G.periodic;
+        if(two_level) {
+            complete = search_two_level<kStride>(P, H, qx, qy, qz, want_all);
+        }
         int rmax;
         if(G.periodic) {
             int gmin = min(G.g[0], min(G.g[1], G.g[2]));
@@ -206,7 +317,7 @@ __global__ void __launch_bounds__(kBlock) knn_kernel(KnnParams P) {
                        max(max(cy, G.g[1] - 1 - cy), max(cz, G.g[2] - 1 - cz)));
         }
         const uint32_t want = want_all;
-        for(int r = 0;; ++r) {
+        for(int r = 0; !two_level; ++r) {
             for(int dz = -r; dz <= r; ++dz) {
                 int z = cz + dz, sz = 0;
                 if(z < 0 || z >= G.g[2]) {
@@ -318,6 +429,8 @@ int run_knn(Ctx* c, const KnnJob& job) {
     P.G = c->grid;
     P.sorted = c->sorted.p;
     P.cell_start = c->cell_start.p;
+    P.sub = c->sub.p;
+    P.vstart = c->vstart.p;
     P.perm = c->perm.p;
     P.n = c->n;
     P.job = job;

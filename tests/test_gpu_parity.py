@@ -104,6 +104,28 @@ def test_knn_clustered_and_flat(Context, port):
     assert (d2 == d2_o).all() and (nbr == nbr_o).all()
 
 
+def test_knn_two_level_grid_clustered(Context, port):
+    """kNN on strongly clustered seeds (density contrast > 1000x): the grid switches to two levels
+    and the search box grows in the fine units of the query's bin; d2 rows bit-equal to the kd-tree
+    oracle (test_nn_search criterion) and finished in milliseconds, not minutes."""
+    n = 400000
+    xyz = oracles.clustered_seeds(n, 99)
+    ctx = Context(0)
+    ctx.set_points(xyz)
+    nbr, d2 = ctx.knn(21)
+    assert ctx.stats()["ms_knn"] < 2000.0
+    idx = np.random.default_rng(0).integers(0, n, 5000)
+    nbq, d2q = port.knn(xyz, 21, queries=xyz[idx])
+    assert (d2[idx] == d2q).all()
+    assert (nbr[idx] == nbq).all()
+    # arbitrary query points, also outside the bounding box of the seeds
+    q = np.random.default_rng(1).random((3000, 3)) * 1.4 - 0.2
+    nb2, dd2 = ctx.knn_points(q, 9)
+    nb3, dd3 = port.knn(xyz, 9, queries=q)
+    assert (dd2 == dd3).all() and (nb2 == nb3).all()
+    ctx.close()
+
+
 def test_knn_ties_and_small(Context, port):
     # lattice: massive exact ties; indices may differ (reference: traversal order), d2 must not
     g = 9
