@@ -437,6 +437,35 @@ def test_volume_conservation_2m(Context):
     assert m3.std() < 0.7 * m.std()
 
 
+def test_full_size_10m_properties(Context):
+    """BASELINE configs[1] and [2] at their full size (10 M seeds, periodic): every cell certified,
+    total volume conserved to 1e-9, bitwise reproducible, and again after a Lloyd iteration and
+    with Laguerre weights (gradient sums to zero)."""
+    n = 10000000
+    xyz = oracles.uniform_seeds(n, 12345)
+    ctx = Context(0)
+    ctx.set_domain_periodic(1.0)
+    ctx.set_points(xyz)
+    ctx.compute_cells()
+    m, mg, st = ctx.get_cells()
+    assert (st == 0).all(), np.bincount(st)
+    assert abs(m.sum() - 1.0) < SUM_TOL and m.min() > 0
+    ctx.compute_cells()
+    m2, mg2, _ = ctx.get_cells()
+    assert (m == m2).all() and (mg == mg2).all()
+    x1 = ctx.lloyd(1)
+    assert x1.min() >= 0.0 and x1.max() < 1.0 + 1e-15
+    h = n ** (-1.0 / 3.0)
+    w = 0.25 * h * h * np.random.default_rng(5).random(n)
+    ctx.set_points(x1, w)
+    ctx.compute_cells()
+    mw, _, stw = ctx.get_cells()
+    assert ((stw & ~np.uint8(4)) == 0).all(), np.bincount(stw)       # Laguerre cells may be empty
+    assert abs(mw.sum() - 1.0) < SUM_TOL
+    assert abs((mw - 1.0 / n).sum()) < 1e-9                          # OTM gradient sums to zero
+    ctx.close()
+
+
 # ---------------------------------------------------------------- edge cases
 def test_edge_cases(Context, port):
     from geogram_b200 import B200VorError
