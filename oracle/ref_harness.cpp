@@ -328,6 +328,33 @@ int georef_cvt_energy(
 }
 
 /*
+ * Delaunay tetrahedra of the unmodified reference (Delaunay::cell_vertex, delaunay/delaunay.h:336-485)
+ * for a non-periodic point set: tets[4*k .. 4*k+3] = vertex indices of finite cell k.
+ * Returns the number of finite cells (only min(count, cap) are written).
+ */
+uint32_t georef_delaunay_tets(uint32_t n, const double* xyz, uint32_t* tets, uint32_t cap) {
+    georef_init(0);
+    GEO::SmartPointer<GEO::PeriodicDelaunay3d> del = new GEO::PeriodicDelaunay3d(false, 1.0);
+    del->set_keeps_infinite(false);
+    del->set_stores_cicl(false);
+    del->set_vertices(n, xyz);
+    del->compute();
+    uint32_t count = 0;
+    for(GEO::index_t c = 0; c < del->nb_cells(); ++c) {
+        if(del->cell_is_infinite(c)) {
+            continue;
+        }
+        if(count < cap) {
+            for(GEO::index_t lv = 0; lv < 4; ++lv) {
+                tets[4 * size_t(count) + lv] = uint32_t(del->cell_vertex(c, lv));
+            }
+        }
+        ++count;
+    }
+    return count;
+}
+
+/*
  * Oracle B ("same algorithm").  Box = [box[0..2], box[3..5]].  k0 = initial
  * neighbour count (reference default 20, delaunay_nn.cpp:49); growth k += k/8
  * (k > 8) else k++, capped at min(kcap, n-1); each growth re-queries the kd-tree

@@ -98,9 +98,22 @@ def cvt_energy():
         print("cvt_energy_%s_3000.npz f=%.15e" % (tag, f.sum()))
 
 
+def delaunay_tets():
+    """Finite Delaunay tetrahedra of the unmodified reference (Delaunay::cell_vertex) on the
+    3000-seed box set: the pin of the tetrahedra exported from the GPU cell vertices."""
+    R = oracles.Reference()
+    xyz = oracles.uniform_seeds(3000, 12345)
+    t = np.sort(R.delaunay_tets(xyz), axis=1)
+    np.savez_compressed(os.path.join(HERE, "delaunay_tets_box_3000.npz"), xyz=xyz, tets=t)
+    print("delaunay_tets_box_3000.npz", t.shape)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "cvt":
         cvt_energy()
+    elif len(sys.argv) > 1 and sys.argv[1] == "tets":
+        delaunay_tets()
     else:
         main()
         cvt_energy()
+        delaunay_tets()

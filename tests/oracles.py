@@ -174,6 +174,17 @@ class Reference(object):
                                        ctypes.c_double(period), _p(f, _cd))
         return f if r == 0 else None
 
+    def delaunay_tets(self, xyz):
+        """Finite Delaunay tetrahedra (n_tets, 4) of a non-periodic point set."""
+        xyz = np.ascontiguousarray(xyz, np.float64)
+        n = xyz.shape[0]
+        cap = 8 * n + 64
+        tets = np.zeros((cap, 4), np.uint32)
+        self.lib.georef_delaunay_tets.restype = ctypes.c_uint32
+        cnt = self.lib.georef_delaunay_tets(ctypes.c_uint32(n), _p(xyz, _cd), _p(tets, _cu), ctypes.c_uint32(cap))
+        assert cnt <= cap
+        return tets[:cnt]
+
     def cells_knn(self, xyz, w=None, box=UNIT_BOX, k0=20, kcap=1000, exact=True,
                   fcap=64, areas=False):
         """Oracle B."""

@@ -100,6 +100,35 @@ def test_export_geometry_on_gpu(tmp_path, periodic):
     ctx.close()
 
 
+@pytest.mark.gpu
+def test_delaunay_tets_vs_reference_golden():
+    """Tetrahedra rebuilt from the GPU cell vertices against Delaunay::cell_vertex of the unmodified
+    reference (golden): every exported tetrahedron is a Delaunay tetrahedron, and every Delaunay
+    tetrahedron whose circumcentre lies inside the clipping box is exported (the others have their
+    Voronoi vertex clipped away by the box)."""
+    from geogram_b200 import Context
+    d = np.load(os.path.join(oracles.ROOT, "tests", "golden", "delaunay_tets_box_3000.npz"))
+    xyz, ref = d["xyz"], d["tets"]
+    n = xyz.shape[0]
+    ctx = Context(0)
+    ctx.set_points(xyz)
+    ctx.compute_cells(want_faces=2)
+    nf, fn, fa = ctx.get_faces()
+    nv, vx, vf = ctx.get_vertices()
+    ours = np.sort(export.delaunay_tets(nv, vf, nf, fn, n), axis=1)
+    key = lambda t: set(map(tuple, t.tolist()))
+    S_ours, S_ref = key(ours), key(ref)
+    assert S_ours <= S_ref
+    P = xyz[ref]                                            # (nt, 4, 3)
+    A = 2.0 * (P[:, 1:] - P[:, :1])
+    b = (P[:, 1:] ** 2).sum(axis=2) - (P[:, :1] ** 2).sum(axis=2)
+    cc = np.linalg.solve(A, b[..., None])[..., 0]
+    inside = ((cc > 1e-9) & (cc < 1 - 1e-9)).all(axis=1)
+    assert key(ref[inside]) <= S_ours
+    assert len(S_ours) > 0.8 * len(S_ref)
+    ctx.close()
+
+
 def oracles_translations():
     """instance -> translation, delaunay/periodic.cpp:44-86 with reorder_instances"""
     T = np.zeros((27, 3))
