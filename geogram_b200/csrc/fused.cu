@@ -13,9 +13,9 @@
 //   power planes                                               delaunay/periodic_delaunay_3d.cpp:3719-3726
 //
 // Design (B200-first):
-//  * A TEAM of G lanes (G = 16: two cells per warp) owns one cell.  All team collectives
-//    are *_sync intrinsics on the team's member mask, so the two teams of a warp run
-//    converged when their control flow agrees and diverge (hardware-managed) when not.
+//  * A TEAM of G lanes (G = 16: two cells per warp) owns one cell.  The two teams of a warp run
+//    in LOCKSTEP: every collective is a full-mask *_sync intrinsic of which a team reads its own
+//    G-lane segment, team-level decisions are predicates, loops run while any team needs them.
 //  * The cell lives in the team's slice of shared memory in DUAL form, densely packed:
 //    slots [0,T) hold the cell vertices as (X,Y,Z,W) homogeneous fp64 coordinates (the
 //    cofactors of the reference's 4x4 determinant), a forward error coefficient, |v|^2 and
@@ -30,11 +30,16 @@
 //    shell is sized from the local density; later shells end at the current
 //    security-radius bound, so a cell costs one scan (relaxed seeds) or two.  The cell is
 //    certified when every candidate with d2 <= bound(R2) was offered and the scanned block
-//    covers that radius; otherwise the block grows by one ring.
+//    covers that radius; otherwise the block grows by one ring.  On a two-level grid
+//    (clustered seeds, grid.cu) the block is measured in the fine units of the seed's own bin
+//    and may grow until it covers the domain (template parameter TWO).
 //  * Exactness: a sign test whose |value| is inside its forward error bound never cuts;
 //    the cell is flagged B200VOR_CELL_UNCERTAIN (same rule as cell.cu).  Cells that exceed
-//    a fixed capacity (slots, planes, ring limit) are flagged and re-done by the legacy
-//    kNN-table pipeline (capi.cu), never silently accepted.
+//    a fixed capacity (slots, planes, ring limit) are flagged and re-done by the large-cell
+//    instance below (one warp per cell), then by the kNN-table pipeline (capi.cu), never
+//    silently accepted.
+//  * The kernel body lives in fused_kernel.inc and is instantiated twice (capacities) x 16
+//    (face lists, event counters, two-level walk, weights as template parameters).
 #include "common.cuh"
 
 #include <stdlib.h>
