@@ -34,6 +34,7 @@ namespace {
 constexpr int kNB = 256;       // reduction blocks
 constexpr int kNT = 256;       // threads per block
 constexpr uint32_t kFcap = 64;
+static_assert(kNB == kNT, "the scalar kernels reduce the kNB partials with one block of kNT threads");
 
 // translation (in periods) of periodic instance `inst`: inverse of translation_to_instance
 __device__ inline void instance_translation(uint32_t inst, int& tx, int& ty, int& tz) {
@@ -209,25 +210,21 @@ __global__ void cg_update_kernel(uint32_t n, const double* __restrict__ sc, cons
     }
 }
 
-// alpha = r.z / p.q from the ordered sum of the partials of p.q
+// alpha = r.z / p.q from the fixed-tree sum of the partials of p.q (one block of kNB threads)
 __global__ void cg_alpha_kernel(const double* __restrict__ part, double* __restrict__ sc) {
-    double pq = 0.0;
-    for(int b = 0; b < kNB; ++b) {
-        pq += part[b];
+    const double pq = block_sum(part[threadIdx.x]);
+    if(threadIdx.x == 0) {
+        const bool stop = sc[kDone] != 0.0 || !(sc[kRR] > sc[kStop]) || !(pq > 0.0);
+        sc[kDone] = stop ? 1.0 : 0.0;
+        sc[kAlpha] = stop ? 0.0 : sc[kRZ] / pq;
     }
-    const bool stop = sc[kDone] != 0.0 || !(sc[kRR] > sc[kStop]) || !(pq > 0.0);
-    sc[kDone] = stop ? 1.0 : 0.0;
-    sc[kAlpha] = stop ? 0.0 : sc[kRZ] / pq;
 }
 
-// beta = (r.z)_new / (r.z)_old from the ordered sums of the partials of the update kernel
+// beta = (r.z)_new / (r.z)_old from the fixed-tree sums of the partials of the update kernel
 __global__ void cg_beta_kernel(const double* __restrict__ part, double* __restrict__ sc) {
-    double rz_new = 0.0, rr = 0.0;
-    for(int b = 0; b < kNB; ++b) {
-        rz_new += part[b];
-        rr += part[kNB + b];
-    }
-    if(sc[kDone] == 0.0) {
+    const double rz_new = block_sum(part[threadIdx.x]);
+    const double rr = block_sum(part[kNB + threadIdx.x]);
+    if(threadIdx.x == 0 && sc[kDone] == 0.0) {
         sc[kBeta] = rz_new / sc[kRZ];
         sc[kRZ] = rz_new;
         sc[kRR] = rr;
@@ -520,9 +517,9 @@ int otm_newton(Ctx* c, const double* nu_in, double* w_io, const b200vor_otm_para
             for(uint32_t t = 0; t < burst; ++t) {
                 otm_spmv_kernel<<<rblk, kNT, 0, st>>>(n, W.nfg.p, W.col.p, W.coef.p, W.p.p, W.q.p);
                 dot_kernel<<<kNB, kNT, 0, st>>>(n, W.p.p, W.q.p, W.part.p);
-                cg_alpha_kernel<<<1, 1, 0, st>>>(W.part.p, sc);
+                cg_alpha_kernel<<<1, kNB, 0, st>>>(W.part.p, sc);
                 cg_update_kernel<<<kNB, kNT, 0, st>>>(n, sc, W.p.p, W.q.p, W.diag.p, W.x.p, W.r.p, W.z.p, W.part.p);
-                cg_beta_kernel<<<1, 1, 0, st>>>(W.part.p, sc);
+                cg_beta_kernel<<<1, kNB, 0, st>>>(W.part.p, sc);
                 cg_dir_kernel<<<nblk, kNT, 0, st>>>(n, sc, W.z.p, W.p.p);
             }
             c->stats.gpu_launches += 6ull * burst;
@@ -539,7 +536,7 @@ int otm_newton(Ctx* c, const double* nu_in, double* w_io, const b200vor_otm_para
         double alpha = 1.0;
         Resid trial = cur;
         bool accepted = false;
-        for(int halv = 0; halv < 40; ++halv) {
+        for(int halv = 0; halv < 16; ++halv) {   // alpha >= 1.5e-5: below that the iterate sits on the rounding floor
             axpy_scatter_kernel<<<nblk, kNT, 0, st>>>(n, c->perm.p, W.w0.p, alpha, W.x.p, W.w1.p);
             c->stats.gpu_launches++;
             if((rc = vec_max(c, W, W.w1.p, &wmax)) || (rc = eval_cells(c, W.w1.p, wmax))) {
