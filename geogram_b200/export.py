@@ -11,6 +11,8 @@ Inputs are the arrays of ``Context.get_faces()`` and ``Context.get_vertices()`` 
                          one Wavefront OBJ with every cell shrunk towards its centroid
 * ``delaunay_tets``   -- the Delaunay tetrahedra (``Delaunay::cell_vertex``, delaunay/delaunay.h:336-485):
                          one per cell vertex = the seed and the three neighbours whose faces meet there
+* ``tet_adjacency``   -- ``Delaunay::cell_adjacent`` (delaunay/delaunay.h:369-380): the tetrahedron across
+                         the facet opposite to each local vertex, -1 on the boundary
 
 Pure index bookkeeping on the host; the geometry (vertex coordinates, face lists) was computed on
 the device.
@@ -112,3 +114,27 @@ def delaunay_tets(nverts, vert_faces, nfaces, face_nbr, n):
     keep = (seed[:, None] < (nb % n)).all(axis=1)
     tets = np.concatenate([seed[keep][:, None], nb[keep]], axis=1)
     return tets.astype(np.uint32)
+
+
+def tet_adjacency(tets):
+    """adj[c, lf] = tetrahedron sharing with c the facet opposite to local vertex lf, or -1
+    (Delaunay::cell_adjacent).  Pure index work: facets are matched by their sorted vertex triples."""
+    tets = np.asarray(tets, np.int64)
+    nt = tets.shape[0]
+    adj = np.full((nt, 4), -1, np.int64)
+    if nt == 0:
+        return adj
+    # facet lf of tet c = its three vertices other than tets[c, lf]
+    lf = np.tile(np.arange(4), nt)
+    c = np.repeat(np.arange(nt), 4)
+    faces = np.stack([np.delete(tets, k, axis=1) for k in range(4)], axis=1).reshape(-1, 3)
+    faces = np.sort(faces, axis=1)
+    order = np.lexsort((faces[:, 2], faces[:, 1], faces[:, 0]))
+    f = faces[order]
+    same = (f[1:] == f[:-1]).all(axis=1)
+    # a facet belongs to at most two tetrahedra of a valid triangulation
+    assert not (same[1:] & same[:-1]).any(), "a facet is shared by more than two tetrahedra"
+    a, b = order[:-1][same], order[1:][same]
+    adj[c[a], lf[a]] = c[b]
+    adj[c[b], lf[b]] = c[a]
+    return adj

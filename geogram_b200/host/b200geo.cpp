@@ -395,6 +395,43 @@ double ConvexCellBatch::total_volume() const {
     return s;
 }
 
+void ConvexCellBatch::tet_adjacency(const std::vector<global_index_t>& tets, std::vector<int64_t>& adjacent) {
+    const size_t nt = tets.size() / 4;
+    adjacent.assign(4 * nt, -1);
+    struct Facet {
+        global_index_t v[3];
+        uint32_t owner;   // 4 c + lf
+    };
+    std::vector<Facet> F(4 * nt);
+    for(size_t c = 0; c < nt; ++c) {
+        for(uint32_t lf = 0; lf < 4; ++lf) {
+            Facet& f = F[4 * c + lf];
+            uint32_t k = 0;
+            for(uint32_t lv = 0; lv < 4; ++lv) {
+                if(lv != lf) {
+                    f.v[k++] = tets[4 * c + lv];
+                }
+            }
+            std::sort(f.v, f.v + 3);
+            f.owner = uint32_t(4 * c + lf);
+        }
+    }
+    std::sort(F.begin(), F.end(), [](const Facet& a, const Facet& b) {
+        if(a.v[0] != b.v[0]) return a.v[0] < b.v[0];
+        if(a.v[1] != b.v[1]) return a.v[1] < b.v[1];
+        if(a.v[2] != b.v[2]) return a.v[2] < b.v[2];
+        return a.owner < b.owner;
+    });
+    for(size_t k = 0; k + 1 < F.size(); ++k) {
+        const Facet &a = F[k], &b = F[k + 1];
+        if(a.v[0] == b.v[0] && a.v[1] == b.v[1] && a.v[2] == b.v[2]) {
+            adjacent[a.owner] = int64_t(b.owner / 4);
+            adjacent[b.owner] = int64_t(a.owner / 4);
+            ++k;
+        }
+    }
+}
+
 // ------------------------------------------------------------------ CentroidalVoronoiTesselation
 CentroidalVoronoiTesselation::CentroidalVoronoiTesselation(coord_index_t dimension) : ctx_(nullptr) {
     if(dimension != 3) {

@@ -161,6 +161,10 @@ public:
     /* Delaunay tetrahedra (Delaunay::cell_vertex, delaunay.h:336-485): 4 vertex ids each
        (periodic: real + N*instance), every tetrahedron once */
     void delaunay_tetrahedra(std::vector<global_index_t>& tets) const;
+    /* Delaunay::cell_adjacent (delaunay.h:369-380) for a list of tetrahedra (4 ids each):
+       adjacent[4 c + lf] = tetrahedron sharing the facet opposite to local vertex lf, or -1.
+       Pure host index work (facets matched by their sorted vertex triples). */
+    static void tet_adjacency(const std::vector<global_index_t>& tets, std::vector<int64_t>& adjacent);
 
 private:
     b200vor_ctx* ctx_;

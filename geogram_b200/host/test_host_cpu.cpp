@@ -1,0 +1,58 @@
+// CPU-only test of the pure-host parts of the mirror (no context is created): tet adjacency.
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <vector>
+
+#include "b200geo.h"
+
+using namespace B200GEO;
+
+static int fails = 0;
+#define EXPECT(c)                                                     \
+    do {                                                              \
+        if(!(c)) {                                                    \
+            printf("FAILED %s:%d: %s\n", __FILE__, __LINE__, #c);     \
+            ++fails;                                                  \
+        }                                                             \
+    } while(0)
+
+int main() {
+    // a fan of tetrahedra around the edge (0,1): ring vertices 2..6, tets (0,1,r_k,r_{k+1})
+    std::vector<global_index_t> tets;
+    const int ring = 5;
+    for(int k = 0; k < ring; ++k) {
+        tets.push_back(0);
+        tets.push_back(1);
+        tets.push_back(global_index_t(2 + k));
+        tets.push_back(global_index_t(2 + (k + 1) % ring));
+    }
+    std::vector<int64_t> adj;
+    ConvexCellBatch::tet_adjacency(tets, adj);
+    EXPECT(adj.size() == size_t(4 * ring));
+    for(int k = 0; k < ring; ++k) {
+        // facets opposite to vertices 0 and 1 are on the boundary; the other two lead around the fan
+        EXPECT(adj[4 * k + 0] == -1 && adj[4 * k + 1] == -1);
+        EXPECT(adj[4 * k + 2] == (k + 1) % ring);          // opposite r_k: shares (0,1,r_{k+1})
+        EXPECT(adj[4 * k + 3] == (k + ring - 1) % ring);   // opposite r_{k+1}: shares (0,1,r_k)
+    }
+    // symmetry on a random soup of face-sharing pairs
+    for(size_t c = 0; c < adj.size() / 4; ++c) {
+        for(int lf = 0; lf < 4; ++lf) {
+            int64_t nb = adj[4 * c + lf];
+            if(nb >= 0) {
+                int back = 0;
+                for(int l2 = 0; l2 < 4; ++l2) {
+                    back += adj[4 * size_t(nb) + l2] == int64_t(c);
+                }
+                EXPECT(back == 1);
+            }
+        }
+    }
+    std::vector<global_index_t> none;
+    ConvexCellBatch::tet_adjacency(none, adj);
+    EXPECT(adj.empty());
+    printf(fails ? "host cpu test: %d FAILURES\n" : "host cpu test: ok\n", fails);
+    return fails ? 1 : 0;
+}

@@ -44,6 +44,32 @@ def test_delaunay_tets_dedup_rule():
     assert len(export.delaunay_tets(nverts, vert_faces, nfaces, face_nbr, 4)) == 0
 
 
+def test_tet_adjacency_on_reference_tets():
+    """Delaunay::cell_adjacent rebuilt from the tetrahedra: on the Delaunay triangulation of the
+    unmodified reference (golden) adjacency is symmetric, adjacent tetrahedra share exactly three
+    vertices, and the boundary facets are those of the convex hull (Euler: interior facets =
+    (4 nt - hull) / 2)."""
+    d = np.load(os.path.join(oracles.ROOT, "tests", "golden", "delaunay_tets_box_3000.npz"))
+    tets = d["tets"].astype(np.int64)
+    adj = export.tet_adjacency(tets)
+    nt = len(tets)
+    c, lf = np.nonzero(adj >= 0)
+    nb = adj[c, lf]
+    assert ((adj[nb] == c[:, None]).sum(axis=1) == 1).all()                  # symmetric
+    shared = np.array([len(set(tets[a]) & set(tets[b])) for a, b in zip(c[:500], nb[:500])])
+    assert (shared == 3).all()
+    hull = int((adj < 0).sum())
+    assert hull > 0 and (4 * nt - hull) % 2 == 0
+    # every hull facet lies on the convex hull: all seeds on one side of its plane
+    xyz = d["xyz"]
+    cc, ll = np.nonzero(adj < 0)
+    for k in range(0, len(cc), max(1, len(cc) // 40)):
+        f = np.delete(tets[cc[k]], ll[k])
+        n = np.cross(xyz[f[1]] - xyz[f[0]], xyz[f[2]] - xyz[f[0]])
+        s = (xyz - xyz[f[0]]) @ n
+        assert (s <= 1e-12).all() or (s >= -1e-12).all()
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("periodic", [True, False])
 def test_export_geometry_on_gpu(tmp_path, periodic):

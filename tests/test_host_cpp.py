@@ -42,6 +42,13 @@ def test_host_library_exports_the_mirrored_interfaces():
     assert "cuda" not in " ".join(undefined).lower()
 
 
+def test_host_pure_functions_on_cpu():
+    """tet adjacency (Delaunay::cell_adjacent) needs no device"""
+    _build()
+    out = subprocess.run([os.path.join(LIB, "test_host_cpu")], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0 and "host cpu test: ok" in out.stdout, out.stdout + out.stderr
+
+
 def test_host_fails_loudly_without_gpu():
     """No CPU fallback: constructing a search object without a CUDA device throws."""
     _build()
