@@ -2,12 +2,17 @@
 """bench.py -- Voronoi cells/s of the hot path on N B200s of one node.
 
 Metric (BASELINE.json): Voronoi cells/sec, device-timed.  A *step* is one CVT Lloyd
-iteration over the whole seed set: counting-sort grid build -> kNN -> warp-per-cell
-clipping with the security radius (+ re-launches of uncertified cells) -> fused fp64
+iteration over the whole seed set: counting-sort grid build -> neighbour walk + per-seed
+cell clipping with the security radius (+ re-launches of the cells a kernel flags) -> fp64
 volume/centroid integration -> seed update.  Workload at N=1: BASELINE configs[1]
-("10M uniform seeds, periodic unit cube, CVT Lloyd iterations on 1 B200"); at N>1 the
-weak-scaling shape of configs[4] (fixed seeds per GPU, every rank holds all seeds, cells
-sharded by seed-index range, updated seeds all-gathered over NCCL each iteration).
+("10M uniform seeds, periodic unit cube, 10 CVT Lloyd iterations on 1 B200") AS WRITTEN: the
+warm-up iterations run on a scratch copy, then the RAW uniform seeds are loaded again and the
+timed steps are Lloyd iterations 1..K from them (`ms_iter` lists every iteration, so the
+dear first iteration and the relaxed steady state are both visible).  At N>1: the
+weak-scaling shape of configs[4] (12.5 M seeds per GPU, cells sharded by x-slab, updated
+seeds all-gathered over NCCL each iteration).  At N=1 the line also carries short
+sub-results for configs[2] (Laguerre pass + OT solve), configs[3] (clustered seeds) and the
+12.5 M-seed point of the weak-scaling curve under `extra_configs`.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--seeds S] [--impl ours|reference]
 
@@ -128,6 +133,112 @@ def run_reference(args, rank):
     print(json.dumps(line))
 
 
+def status_hist(st):
+    """per-status cell counts from a status byte array (torch tensor on any device)"""
+    names = {1: "uncertified", 2: "uncertain", 4: "empty", 8: "boxface", 16: "overflow",
+             32: "duplicate", 64: "degenerate"}
+    out = {"ok": int((st == 0).sum().item())}
+    for bit, nm in names.items():
+        out[nm] = int(((st & bit) != 0).sum().item())
+    return out
+
+
+def clustered_seeds_device(torch, n, dev, seed=12345, nclusters=32):
+    """BASELINE configs[3] generator on the device: mixture of 32 isotropic Gaussians, centres
+    0.1 + 0.8 U, sigma 0.005 + 0.045 U, rejected to (0,1)^3."""
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(seed)
+    c = 0.1 + 0.8 * torch.rand((nclusters, 3), dtype=torch.float64, device=dev, generator=gen)
+    s = 0.005 + 0.045 * torch.rand((nclusters,), dtype=torch.float64, device=dev, generator=gen)
+    out = []
+    have = 0
+    while have < n:
+        k = torch.randint(0, nclusters, (n,), device=dev, generator=gen)
+        p = c[k] + s[k, None] * torch.randn((n, 3), dtype=torch.float64, device=dev, generator=gen)
+        p = p[((p > 0) & (p < 1)).all(dim=1)]
+        out.append(p)
+        have += p.shape[0]
+    return torch.cat(out)[:n].contiguous()
+
+
+def extra_configs(torch, dev, ctx, xyz_relaxed, n, args):
+    """Short driver-visible sub-results for the configs the headline does not time (N=1 only)."""
+    from geogram_b200 import Context
+    import numpy as np
+    res = {}
+    # ---- configs[2]: Laguerre cells with random weights on the relaxed seeds: volumes + weight
+    #      gradient g_i = vol_i - 1/n (one pass), then the full semi-discrete OT solve ----
+    h = n ** (-1.0 / 3.0)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(5)
+    w = 0.25 * h * h * torch.rand((n,), dtype=torch.float64, device=dev, generator=gen)
+    ctx.set_points_device(n, xyz_relaxed.data_ptr(), w.data_ptr())
+    ctx.compute_cells(want_faces=True)
+    ctx.compute_cells(want_faces=True)              # second pass = warm
+    s = ctx.stats()
+    m = torch.empty((n,), dtype=torch.float64, device=dev)
+    st = torch.empty((n,), dtype=torch.uint8, device=dev)
+    ctx.get_cells_device(m.data_ptr(), None, st.data_ptr())
+    grad = m - 1.0 / n
+    lag = {"workload": "BASELINE configs[2]: %d seeds after the timed Lloyd iterations, weights 0.25 h^2 U(0,1), "
+                       "periodic; volumes + facet areas + gradient vol_i - 1/n, one pass" % n,
+           "ms_grid": s["ms_grid"], "ms_cells": s["ms_clip"] + s["ms_knn"],
+           "cells_per_s": n / (1e-3 * (s["ms_grid"] + s["ms_clip"] + s["ms_knn"])),
+           "status": status_hist(st), "sum_m_minus_1": float(m.sum().item() - 1.0),
+           "grad_sum": float(grad.sum().item()), "grad_norm2": float(torch.sqrt((grad * grad).sum()).item()),
+           "cells_per_pass": s["n_pass"][: s["passes"]]}
+    res["configs2_laguerre_pass"] = lag
+    if not args.no_otm:
+        ctx.set_points_device(n, xyz_relaxed.data_ptr())
+        w0 = w.cpu().numpy()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        _, r = ctx.otm_newton(None, w0=w0, epsilon=1e-3)
+        wall = time.perf_counter() - t0
+        r["wall_s"] = wall
+        r["workload"] = "BASELINE configs[2]: semi-discrete OT solve, uniform target, start weights 0.25 h^2 U(0,1), epsilon 1e-3"
+        res["configs2_otm_solve"] = r
+    del w, m, st, grad
+    # ---- configs[3]: clustered Gaussian-mixture seeds in the unit box (security-radius retries,
+    #      two-level grid), one cell pass ----
+    nc = args.clustered
+    if nc > 0:
+        xyz = clustered_seeds_device(torch, nc, dev)
+        c2 = Context(dev.index)
+        c2.set_domain_box([0, 0, 0, 1, 1, 1])
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        c2.set_points_device(nc, xyz.data_ptr())
+        c2.compute_cells()
+        wall = time.perf_counter() - t0
+        s = c2.stats()
+        m = torch.empty((nc,), dtype=torch.float64, device=dev)
+        st = torch.empty((nc,), dtype=torch.uint8, device=dev)
+        c2.get_cells_device(m.data_ptr(), None, st.data_ptr())
+        res["configs3_clustered"] = {
+            "workload": "BASELINE configs[3] on one GPU: %d Gaussian-mixture seeds (32 clusters), unit box, one cell pass" % nc,
+            "ms_grid": s["ms_grid"], "ms_cells": s["ms_clip"] + s["ms_knn"], "wall_s": wall,
+            "cells_per_s": nc / (1e-3 * (s["ms_grid"] + s["ms_clip"] + s["ms_knn"])),
+            "status": status_hist(st), "sum_m_minus_1": float(m.sum().item() - 1.0),
+            "cells_per_pass": s["n_pass"][: s["passes"]], "k_pass": s["k_pass"][: s["passes"]],
+            "grid": s["grid_dim"]}
+        c2.close()
+    return res
+
+
+def load_inst_counts(n_cells):
+    """Per-iteration instruction counts of the cell kernels from the committed ncu capture
+    (profiles/r02_inst_by_iter.json, made by tools/ncu_inst_by_iter.sh from THIS bench command:
+    same seeds, same iterations -> same counts)."""
+    p = os.path.join(ROOT, "profiles", "r02_inst_by_iter.json")
+    if not os.path.exists(p):
+        return None
+    d = json.load(open(p))
+    if int(d.get("seeds", 0)) != n_cells:
+        return None
+    return d
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -137,6 +248,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=1000000)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra_configs sub-results")
+    ap.add_argument("--no-otm", action="store_true", help="skip the OT solve of extra_configs")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
+    ap.add_argument("--clustered", type=int, default=10000000, help="seeds of the configs[3] sub-result (0 = skip)")
     ap.add_argument("--k0", type=int, default=0)
     ap.add_argument("--mode", type=int, default=0)
     ap.add_argument("--ppc", type=float, default=0.0)
@@ -156,7 +271,7 @@ def main():
     json_fd = os.dup(1)
     os.dup2(2, 1)
 
-    import numpy as np
+    import numpy as np  # noqa: F401
     import torch
     from geogram_b200 import Context
 
@@ -172,27 +287,27 @@ def main():
     n_total = n_per * world
 
     # synthetic seeds: uniform in the periodic unit cube, generated on the device
-    gen = torch.Generator(device=dev)
-    gen.manual_seed(12345 + rank)
-    mine = torch.rand((n_per, 3), dtype=torch.float64, device=dev, generator=gen)
-    full = torch.empty((n_total, 3), dtype=torch.float64, device=dev)
-    if world > 1:
+    def raw_seeds(n_per_rank):
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(12345 + rank)
+        mine = torch.rand((n_per_rank, 3), dtype=torch.float64, device=dev, generator=gen)
+        if world == 1:
+            return mine
+        full = torch.empty((n_per_rank * world, 3), dtype=torch.float64, device=dev)
         dist.all_gather_into_tensor(full, mine)
-    else:
-        full.copy_(mine)
-    del mine
+        return full
+
+    full0 = raw_seeds(n_per)       # pristine raw seeds: the timed run starts from these
 
     stream = torch.cuda.current_stream()
     ctx = Context(local_rank)
     ctx.set_domain_periodic(1.0)
     if args.ppc > 0:
         ctx.set_points_per_cell(args.ppc)
+    peaks = ctx.microbench() if rank == 0 else None
     from geogram_b200.sharding import ShardedLloyd
     job = ShardedLloyd(ctx, n_total, dist if world > 1 else None, dev, stream)
     lo, hi = job.first, job.last
-    # N>1: rows re-ordered once into x-quantile slabs, so that rank r owns a spatial slab
-    job.set_seeds_device(full, slabs=world > 1)
-    del full
 
     def step():
         job.step(k0=args.k0, mode=args.mode)
@@ -202,8 +317,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ---- warm-up on a scratch copy: Lloyd iterations 1..W from the raw seeds ----
+    # N>1: rows re-ordered once into x-quantile slabs, so that rank r owns a spatial slab
+    job.set_seeds_device(full0, slabs=world > 1)
     for _ in range(args.warmup):
         step()
+    # ---- the timed run: the raw seeds again, Lloyd iterations 1..K ----
+    job.set_seeds_device(full0, slabs=world > 1)
     launches0 = ctx.stats()["gpu_launches"]
     job.phase = {k: 0.0 for k in job.phase}
     job.comm_ms()
@@ -211,114 +331,129 @@ def main():
     if sampler:
         sampler.start()
     barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(args.steps):
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    clip_iter = []
+    evs[0].record(stream)
+    for k in range(args.steps):
+        before = job.phase["ms_clip"]
         step()
-    e1.record(stream)
+        clip_iter.append(job.phase["ms_clip"] - before)
+        evs[k + 1].record(stream)
     barrier()
-    ms = e0.elapsed_time(e1)
+    ms = evs[0].elapsed_time(evs[-1])
+    ms_iter = [evs[k].elapsed_time(evs[k + 1]) for k in range(args.steps)]
     clocks = sampler.summary() if sampler else None
     launches = ctx.stats()["gpu_launches"] - launches0
     last = ctx.stats()
     phase = dict(job.phase)
     phase["ms_allgather"] = job.comm_ms()
     if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        t = torch.tensor([ms] + ms_iter, dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+        ms = float(t[0].item())
+        ms_iter = [float(x) for x in t[1:].tolist()]
     value = n_total * args.steps / (ms * 1e-3)
 
     # ---- end to end through the public API with HOST buffers (pinned): every step uploads this
     #      rank's rows (H2D), exchanges them over NVLink (N>1), runs the Lloyd iteration and reads
-    #      this rank's updated rows back (D2H) ----
-    e2e_steps = min(args.steps, 5)
-    host_in = torch.empty((hi - lo, 3), dtype=torch.float64).pin_memory()
-    host_out = torch.empty((hi - lo, 3), dtype=torch.float64).pin_memory()
-    job.get_shard_host(host_in)        # the seeds as relaxed by the timed steps
+    #      this rank's updated rows back (D2H).  Iterations K+1.. of the same run. ----
+    e2e_value, e2e_steps = None, 0
+    if not args.no_e2e:
+        e2e_steps = min(args.steps, 5)
+        host_in = torch.empty((hi - lo, 3), dtype=torch.float64).pin_memory()
+        host_out = torch.empty((hi - lo, 3), dtype=torch.float64).pin_memory()
+        # start again from the raw seeds: this rank's rows of the (slab-ordered) raw array
+        raw_rows = full0 if job.order is None else full0[job.order]
+        host_in.copy_(raw_rows[lo:hi])
+        del raw_rows
+        torch.cuda.synchronize()
 
-    def e2e_step():
-        job.set_shard_host(host_in)
-        job.step(k0=args.k0, mode=args.mode)
-        job.get_shard_host(host_out)
+        def e2e_step():
+            job.set_shard_host(host_in)
+            job.step(k0=args.k0, mode=args.mode)
+            job.get_shard_host(host_out)
+            host_in.copy_(host_out)      # the next iteration starts from this one's result
 
-    e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e_value = n_total * e2e_steps / e2e_s
-    del host_in, host_out
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t.item())
+        e2e_value = n_total * e2e_steps / e2e_s
+        del host_in, host_out
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (per launch), HBM peak from MEASURED_PEAKS.json ----
-    # The dominant kernel is cells_fused_kernel (one launch per step).  Its duration is
-    # measured live with CUDA events recorded by the library on the launching stream
-    # (stats ms_clip).  Algorithmic HBM bytes per cell: read Seed 32 + perm 4
-    # + cell_start 4/ppc, write m 8 + mg 24 + status 1.
-    peak, peak_src = load_peaks()
+    # ---- rooflines of the dominant kernel (the first-pass cell kernel, one launch per step) ----
+    # Kernel time: CUDA events recorded by the library on the launching stream (stats ms_clip,
+    # summed over the K timed iterations).  Every numerator below is taken at the SAME seed
+    # states as the timed launches: the flop-model event counts come from an untimed replay of
+    # iterations 1..K (event-counting instance of the same kernel), the instruction counts from
+    # the committed ncu capture of this very command (profiles/r02_inst_by_iter.json).
+    hbm_peak, hbm_src = load_peaks()
     per_step = {k: v / args.steps for k, v in phase.items()}
     n_cells = n_per
     ppc_used = args.ppc if args.ppc > 0 else 8.0
     bytes_per_cell = 32.0 + 4.0 + 4.0 / ppc_used + 8.0 + 24.0 + 1.0
-    fused = last["k_pass"][0] == 0
-    if fused:
-        kernel, kms = "cells_fused_kernel", per_step["ms_clip"]
-        alg_bytes = bytes_per_cell * n_cells
-    else:
-        k_eff = last["k_pass"][0] + 1
-        dom = max(("ms_knn", "ms_clip"), key=lambda k: per_step[k])
-        kernel = {"ms_knn": "knn_kernel", "ms_clip": "cells_knn_kernel"}[dom]
-        kms = per_step[dom]
-        alg_bytes = ((32.0 + 4 * k_eff) if dom == "ms_knn" else (69.0 + 4 * k_eff)) * n_cells
-    achieved = alg_bytes / (kms * 1e-3) / 1e9
-    traffic = None
+    kms_total = sum(clip_iter)
+    kernel = "cells_tpc_kernel" if last.get("tpc_cells", 0) else "cells_fused_kernel"
+    flop_iter = []
+    ev_tot = {"sum_planes": 0, "sum_tests": 0, "sum_created": 0, "sum_tets": 0, "sum_scans": 0}
+    if world == 1:
+        job.set_seeds_device(full0)
+        for k in range(args.steps):
+            ctx.compute_cells(mode=args.mode)
+            ev = ctx.stats()
+            flop_iter.append(12.0 * ev["sum_planes"] + 7.0 * ev["sum_tests"] + 64.0 * ev["sum_created"]
+                             + 45.0 * ev["sum_tets"])
+            for key in ev_tot:
+                ev_tot[key] += ev[key]
+            step()
+    flops = sum(flop_iter)
+    ach_tf = flops / (kms_total * 1e-3) / 1e12 if flops else None
     issue = None
-    tpath = os.path.join(ROOT, "profiles", "r01_fused_traffic.json")
-    if fused and os.path.exists(tpath):
-        tj = json.load(open(tpath))
-        if int(tj.get("seeds", 0)) == n_cells:
-            traffic = tj["dram_bytes_per_launch"]     # ncu --set full, dram__bytes_read+write
-        if "warp_inst_per_launch" in tj:
-            # issue-slot roofline (north_star: "FP32 issue-rate roofline"): warp instructions per
-            # cell from the committed ncu capture x the cells of one launch / the LIVE kernel
-            # time, against 4 schedulers x SMs x max SM clock (one warp instruction per cycle each)
-            props = torch.cuda.get_device_properties(local_rank)
-            ipc = tj["warp_inst_per_launch"] / float(tj["seeds"])
-            peak_issue = 4.0 * props.multi_processor_count * (clocks or {}).get("sm_max_mhz", 1965.0) * 1e6
-            ach = ipc * n_cells / (kms * 1e-3)
-            issue = {"warp_inst_per_cell": ipc, "achieved_ginst_s": ach / 1e9,
-                     "peak_ginst_s": peak_issue / 1e9, "frac": ach / peak_issue,
-                     "thread_inst_per_warp_inst": tj.get("thread_inst_per_warp_inst"),
-                     "source": "instruction count: " + tj["source"] + "; time: live CUDA events"}
-    # flop model of SURVEY 8(d): 12 P + 7 C + 64 V + 45 I per cell, from the event counters of
-    # one untimed compute_cells() call on the same seeds
-    ctx.compute_cells()
-    ev = ctx.stats()
-    flops = 12.0 * ev["sum_planes"] + 7.0 * ev["sum_tests"] + 64.0 * ev["sum_created"] + 45.0 * ev["sum_tets"]
-    roofline = {"kernel": kernel, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "kernel_ms_per_launch": kms, "algorithmic_bytes_per_cell": bytes_per_cell,
-                "flop_model": {"sum_planes": ev["sum_planes"], "sum_tests": ev["sum_tests"],
-                               "sum_created": ev["sum_created"], "sum_tets": ev["sum_tets"],
-                               "grid_scans_per_cell": ev["sum_scans"] / max(n_cells, 1),
-                               "flop_per_cell": flops / max(n_cells, 1),
-                               "achieved_tflops": flops / (kms * 1e-3) / 1e12,
-                               "fp64_peak_tflops_nominal": 37.0},
-                "issue_rate": issue,
-                "note": "issue/latency-bound kernel (see issue_rate; fp64 pipe ~10%); neither DRAM nor "
-                        "tensor bound: the hbm fraction is reported because the contract asks for one, "
-                        "see DESIGN.md 4.2 and profiles/"}
+    inst = load_inst_counts(n_cells) if world == 1 else None
+    if inst and len(inst["iters"]) >= args.steps:
+        wi = sum(it["warp_inst"] for it in inst["iters"][: args.steps])
+        ti = sum(it["thread_inst"] for it in inst["iters"][: args.steps])
+        ach = wi / (kms_total * 1e-3)
+        issue = {"warp_inst_per_cell": wi / (float(n_cells) * args.steps),
+                 "thread_inst_per_warp_inst": ti / float(wi),
+                 "achieved_ginst_s": ach / 1e9, "peak_ginst_s": peaks["issue_ginst_s"],
+                 "frac": ach / 1e9 / peaks["issue_ginst_s"],
+                 "source": "instruction counts per iteration: " + inst.get("source", "profiles/r02_inst_by_iter.json")
+                           + " (same seeds and iterations as this run); time: live CUDA events"}
+    traffic = inst.get("dram_bytes_per_launch") if inst else None
+    ach_bw = bytes_per_cell * n_cells * args.steps / (kms_total * 1e-3) / 1e9
+    roofline = {
+        "kernel": kernel, "bound": "fp64", "unit": "TFLOP/s",
+        "achieved": ach_tf, "peak": peaks["fp64_tflops"],
+        "frac": (ach_tf / peaks["fp64_tflops"]) if ach_tf else None,
+        "traffic": traffic,
+        "peak_source": "fp64/fp32: FMA-chain microbench in this process (b200vor_microbench); hbm: " + hbm_src,
+        "kernel_ms_per_launch": kms_total / args.steps, "kernel_ms_by_iter": clip_iter,
+        "flop_model": {"formula": "12 P + 7 C + 64 V + 45 I (SURVEY 8(d)), summed over the K timed iterations "
+                                  "(untimed replay with the event-counting kernel instance)",
+                       "sum_planes": ev_tot["sum_planes"], "sum_tests": ev_tot["sum_tests"],
+                       "sum_created": ev_tot["sum_created"], "sum_tets": ev_tot["sum_tets"],
+                       "grid_scans_per_cell": ev_tot["sum_scans"] / max(n_cells * args.steps, 1),
+                       "flop_per_cell_by_iter": [f / n_cells for f in flop_iter],
+                       "frac_of_fp32_peak": (ach_tf / peaks["fp32_tflops"]) if ach_tf else None},
+        "peaks_measured": peaks,
+        "hbm": {"achieved": ach_bw, "peak": hbm_peak, "unit": "GB/s", "frac": ach_bw / hbm_peak,
+                "algorithmic_bytes_per_cell": bytes_per_cell},
+        "issue_rate": issue,
+        "note": "the cell kernel is issue/latency bound: `frac` is the SURVEY 8(d) flop model against the measured "
+                "FP64 FMA peak, `issue_rate` the share of the 4 x SMs x clock issue slots it fills, `hbm` the "
+                "algorithmic bytes against the measured copy bandwidth (DESIGN.md section 4)"}
 
     cpu = None
     if world == 1 and not args.no_cpu:
@@ -327,15 +462,45 @@ def main():
                "sample": "%d uniform seeds, periodic, 2 Lloyd iterations "
                          "(Delaunay + cell extraction + compute_mg + update)" % args.cpu_sample}
 
+    extra = None
+    if world == 1 and not args.no_extra:
+        # the seeds as relaxed by the K iterations of the replay above
+        xyz_relaxed = job.full.clone()
+        ctx.lloyd_device(0, xyz_relaxed.data_ptr())
+        extra = extra_configs(torch, dev, ctx, xyz_relaxed, n_cells, args)
+        del xyz_relaxed
+        # 12.5 M-seed point of the weak-scaling curve (configs[4] at N=1): 3 iterations from raw seeds
+        n_w = 12500000
+        if n_cells != n_w:
+            full_w = raw_seeds(n_w)
+            job_w = ShardedLloyd(ctx, n_w, None, dev, stream)
+            job_w.set_seeds_device(full_w)
+            job_w.step()
+            job_w.set_seeds_device(full_w)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            for _ in range(3):
+                job_w.step()
+            b.record(stream)
+            torch.cuda.synchronize()
+            extra["configs4_weak_n1"] = {"workload": "12.5 M uniform periodic seeds on 1 GPU, Lloyd iterations 1..3 from raw seeds",
+                                         "seeds": n_w, "ms_per_step": a.elapsed_time(b) / 3,
+                                         "cells_per_s": n_w * 3 / (a.elapsed_time(b) * 1e-3)}
+            del full_w, job_w
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "ms_iter": ms_iter,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "BASELINE configs[1]: uniform seeds, periodic unit cube, one CVT "
-                               "Lloyd iteration per step" if world == 1 else
-                               "BASELINE configs[4]: weak scaling, uniform periodic, one Lloyd "
-                               "iteration per step, x-quantile slab per rank, seeds all-gathered over NCCL",
+        "config": {"workload": "BASELINE configs[1]: %d uniform seeds, periodic unit cube, CVT Lloyd iterations "
+                               "1..%d from the raw seeds (warm-up ran on a scratch copy)" % (n_total, args.steps)
+                               if world == 1 else
+                               "BASELINE configs[4]: weak scaling, %d uniform periodic seeds per GPU, Lloyd iterations "
+                               "1..%d from the raw seeds, x-quantile slab per rank, seeds all-gathered over NCCL"
+                               % (n_per, args.steps),
                    "seeds_per_gpu": n_per, "seeds_total": n_total,
                    "k_pass": last["k_pass"][: last["passes"]],
                    "cells_per_pass": last["n_pass"][: last["passes"]],
@@ -343,9 +508,12 @@ def main():
                    "l2": "inputs (>= 240 MB/step) exceed the 126 MB L2"},
         "phase_ms_per_step": per_step,
         "roofline": roofline, "cpu_baseline": cpu,
-        "e2e": {"value": e2e_value, "unit": UNIT, "steps": e2e_steps,
+        "e2e": None if e2e_value is None else
+               {"value": e2e_value, "unit": UNIT, "steps": e2e_steps,
                 "h2d_bytes_per_step": 24 * n_total, "d2h_bytes_per_step": 24 * n_total,
-                "note": "whole job: every rank moves its own rows (24 B/seed each way)"},
+                "note": "whole job, Lloyd iterations 1..%d from the raw seeds: every rank uploads its own rows from "
+                        "pinned host memory and reads them back each step (24 B/seed each way)" % e2e_steps},
+        "extra_configs": extra,
         "gpu_launches": int(launches), "clocks": clocks,
     }
     sys.stdout.flush()

@@ -29,6 +29,7 @@ EXPORTS = [
     "b200vor_knn", "b200vor_knn_points", "b200vor_compute_cells", "b200vor_get_cells",
     "b200vor_get_faces", "b200vor_get_vertices", "b200vor_get_cvt", "b200vor_otm_newton", "b200vor_get_spatial_order", "b200vor_lloyd", "b200vor_get_stats",
     "b200vor_set_points_per_cell", "b200vor_set_stream", "b200vor_set_query_range",
+    "b200vor_microbench",
 ]
 
 
@@ -81,6 +82,12 @@ class Stats(ctypes.Structure):
         return d
 
 
+class Peaks(ctypes.Structure):
+    _fields_ = [("fp64_tflops", ctypes.c_double), ("fp32_tflops", ctypes.c_double),
+                ("issue_ginst_s", ctypes.c_double), ("sm_clock_mhz", ctypes.c_double),
+                ("sm_count", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
+
+
 class B200VorError(RuntimeError):
     pass
 
@@ -120,6 +127,7 @@ def load_library():
     lib.b200vor_set_points_per_cell.argtypes = [vp, dbl]
     lib.b200vor_set_stream.argtypes = [vp, vp]
     lib.b200vor_set_query_range.argtypes = [vp, u32, u32]
+    lib.b200vor_microbench.argtypes = [vp, ctypes.POINTER(Peaks)]
     _lib = lib
     return lib
 
@@ -282,6 +290,12 @@ class Context(object):
         self._check(self.lib.b200vor_lloyd(
             self.h, int(iters), ctypes.byref(p),
             _ptr(int(xyz_out_ptr)) if xyz_out_ptr else None, 1))
+
+    def microbench(self):
+        """Measured FP64 / FP32 FMA throughput and the issue-slot peak of this GPU (dict)."""
+        p = Peaks()
+        self._check(self.lib.b200vor_microbench(self.h, ctypes.byref(p)))
+        return {name: getattr(p, name) for name, _ in p._fields_ if name != "reserved"}
 
     def stats(self):
         s = Stats()

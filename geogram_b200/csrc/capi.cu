@@ -372,7 +372,14 @@ int b200vor_create(b200vor_ctx** out, int device) {
     B200_CUDA_CHECK(cudaSetDevice(device));
     b200vor_ctx* h = new b200vor_ctx();
     h->c.device = device;
-    B200_CUDA_CHECK(cudaStreamCreateWithFlags(&h->c.stream, cudaStreamNonBlocking));
+    {
+        cudaError_t se = cudaStreamCreateWithFlags(&h->c.stream, cudaStreamNonBlocking);
+        if(se != cudaSuccess) {
+            set_error("b200vor_create: cudaStreamCreateWithFlags -> %s", cudaGetErrorString(se));
+            delete h;
+            return B200VOR_ERR_CUDA;
+        }
+    }
     h->c.own_stream = true;
     *out = h;
     return B200VOR_OK;
@@ -826,6 +833,16 @@ int b200vor_get_spatial_order(b200vor_ctx* h, uint32_t* order, int on_device) {
     }
     B200_CUDA_CHECK(cudaStreamSynchronize(c->stream));
     return B200VOR_OK;
+}
+
+int b200vor_microbench(b200vor_ctx* h, b200vor_peaks* peaks) {
+    if(!h || !peaks) {
+        set_error("b200vor_microbench: null argument");
+        return B200VOR_ERR_ARG;
+    }
+    B200_CUDA_CHECK(cudaSetDevice(h->c.device));
+    memset(peaks, 0, sizeof(*peaks));
+    return microbench(&h->c, peaks);
 }
 
 int b200vor_get_stats(b200vor_ctx* h, b200vor_stats* stats) {

@@ -197,5 +197,7 @@ int compact_failed(Ctx* c, const uint32_t* qlist_in, uint32_t nq_in, uint32_t* q
 int lloyd_update(Ctx* c);
 int select_range(Ctx* c, uint32_t* qout, uint32_t* count_out_host);
 int reduce_events(Ctx* c);
+// microbench.cu
+int microbench(Ctx* c, b200vor_peaks* out);
 
 }  // namespace b200vor

@@ -95,11 +95,12 @@ class ShardedLloyd(object):
         slabs=True first re-orders the rows into x-quantile slabs (`slab_order`); the permutation
         is kept in `self.order` (row k of the job is row order[k] of the caller)."""
         self.order = None
-        if slabs:
-            self.order = slab_order(full)
-            self.full.copy_(full[self.order])
-        else:
-            self.full.copy_(full)
+        with self._on_stream():
+            if slabs:
+                self.order = slab_order(full)
+                self.full.copy_(full[self.order])
+            else:
+                self.full.copy_(full)
         self.ctx.set_points_device(self.n_total, self.full.data_ptr())
         self._stale = False
         self._take("ms_grid")
@@ -108,9 +109,10 @@ class ShardedLloyd(object):
         """host_rows: this rank's rows as a (last-first,3) float64 host tensor (pinned for speed).
         H2D of the own rows only; the other ranks' rows arrive over NVLink."""
         mine = self.full[self.first:self.last]
-        mine.copy_(host_rows, non_blocking=True)
-        if self.world > 1:
-            self._gather(mine)
+        with self._on_stream():
+            mine.copy_(host_rows, non_blocking=True)
+            if self.world > 1:
+                self._gather(mine)
         self.ctx.set_points_device(self.n_total, self.full.data_ptr())
         self._stale = False
         self._take("ms_grid")
@@ -132,14 +134,16 @@ class ShardedLloyd(object):
         self._refresh()
         self.ctx.lloyd_device(1, self.out.data_ptr(), k0=k0, mode=mode)
         self._take("ms_knn", "ms_clip")
-        self._gather(self.out[self.first:self.last])
+        with self._on_stream():
+            self._gather(self.out[self.first:self.last])
         self._stale = True          # the grid of the new seeds is built lazily (_refresh)
 
     def get_shard_host(self, host_rows):
         """Own rows of the current seeds -> host tensor (D2H of the own rows only)."""
         if self.world == 1:
             self.ctx.lloyd_device(0, self.full.data_ptr())
-        host_rows.copy_(self.full[self.first:self.last], non_blocking=True)
+        with self._on_stream():
+            host_rows.copy_(self.full[self.first:self.last], non_blocking=True)
         if self.on_gpu:
             self.stream.synchronize()
         return host_rows
@@ -154,6 +158,14 @@ class ShardedLloyd(object):
         return ms
 
     # ---- internals ----
+    def _on_stream(self):
+        """Every torch op of the job (copies, NCCL) is issued on the stream the context is bound
+        to, whatever torch's current stream is at call time."""
+        if self.on_gpu:
+            return self.torch.cuda.stream(self.stream)
+        import contextlib
+        return contextlib.nullcontext()
+
     def _gather(self, mine):
         if not self.on_gpu:
             allgather_rows(self.dist, self.full, mine)

@@ -207,6 +207,18 @@ int b200vor_get_spatial_order(b200vor_ctx* ctx, uint32_t* order, int on_device);
 
 /* ---- introspection ---- */
 int b200vor_get_stats(b200vor_ctx* ctx, b200vor_stats* stats);
+
+/* measured pipe peaks of the context's GPU (FMA chains timed with CUDA events): the denominators
+ * of the flop / issue rooflines of the cell kernels (no reference counterpart; the reference's
+ * Stopwatch / PredicateStats play this role on the CPU, basic/stopwatch.h:69, predicates.cpp:353) */
+typedef struct b200vor_peaks {
+    double fp64_tflops;     /* DFMA, 2 flop each                                   */
+    double fp32_tflops;     /* FFMA, 2 flop each                                   */
+    double issue_ginst_s;   /* 4 schedulers x SMs x max SM clock, warp instructions */
+    double sm_clock_mhz;
+    uint32_t sm_count, reserved;
+} b200vor_peaks;
+int b200vor_microbench(b200vor_ctx* ctx, b200vor_peaks* peaks);
 /* tuning knob: target points per grid cell (default 8.0); takes effect at the next set_points */
 int b200vor_set_points_per_cell(b200vor_ctx* ctx, double ppc);
 
