@@ -70,7 +70,7 @@ class Stats(ctypes.Structure):
         ("sum_created", ctypes.c_uint64), ("sum_tets", ctypes.c_uint64),
         ("gpu_launches", ctypes.c_uint64),
         ("grid_dim", ctypes.c_uint32 * 3),
-        ("reserved0", ctypes.c_uint32),
+        ("tpc_cells", ctypes.c_uint32),
         ("sum_scans", ctypes.c_uint64),
     ]
 

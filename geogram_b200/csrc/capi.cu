@@ -197,18 +197,42 @@ int cells_pipeline(Ctx* c, const b200vor_cell_params* params, bool collect_event
     memset(c->stats.n_pass, 0, sizeof(c->stats.n_pass));
     memset(c->stats.k_pass, 0, sizeof(c->stats.k_pass));
     int pass0 = 0;
-    if(p.mode != 2) {
-        // fused grid walk: one launch, no neighbour table (fused.cu)
+    c->stats.tpc_cells = 0;
+    if(p.mode == 0 && !p.want_faces && !p.want_energy && tpc_applicable(c)) {
+        // thread-per-cell kernel (tpc.cu): one launch; what it flags goes to the team kernel
         T.mark(2);
-        if((rc = run_cells_fused(c, nq, qlist, int(p.want_faces), collect_events ? 1 : 0, 0.f,
-                                 int(p.want_energy), 0))) {
+        if((rc = run_cells_tpc(c, nq, qlist, collect_events ? 1 : 0))) {
             return rc;
         }
         T.mark(0);
         c->stats.n_pass[0] = nq;
         c->stats.k_pass[0] = 0;
         c->stats.passes = 1;
+        c->stats.tpc_cells = nq;
         pass0 = 1;
+        if((rc = c->qlist.reserve(nq)) || (rc = c->qlist2.reserve(nq))) {
+            return rc;
+        }
+        uint32_t* out = (qlist == c->qlist.p) ? c->qlist2.p : c->qlist.p;
+        uint32_t nfail = 0;
+        if((rc = compact_failed(c, qlist, nq, out, nullptr, &nfail,
+                                B200VOR_CELL_UNCERTIFIED | B200VOR_CELL_OVERFLOW))) {
+            return rc;
+        }
+        qlist = out;
+        nq = nfail;
+    }
+    if(p.mode != 2 && nq > 0) {
+        // team-kernel grid walk: one launch, no neighbour table (fused.cu)
+        T.mark(2);
+        if((rc = run_cells_fused(c, nq, qlist, int(p.want_faces), collect_events ? 1 : 0, 0.f,
+                                 int(p.want_energy), 0))) {
+            return rc;
+        }
+        T.mark(0);
+        c->stats.n_pass[pass0] = nq;
+        c->stats.k_pass[pass0] = 0;
+        c->stats.passes = ++pass0;
         if(p.mode == 1) {
             nq = 0;
         } else {

@@ -7,6 +7,7 @@
 #include <string>
 
 #include "../../include/b200vor.h"
+#include "grid_types.h"
 
 namespace b200vor {
 
@@ -22,38 +23,6 @@ void set_error(const char* fmt, ...);
         }                                                                           \
     } while(0)
 
-// Uniform grid over the domain.  Cell id = ix + gx*(iy + gy*iz): x is the fastest
-// axis, so a run of cells along x is one contiguous span of the sorted point array.
-struct GridDesc {
-    double lo[3];
-    double w[3];       // cell width
-    double inv_w[3];
-    int g[3];
-    int periodic;
-    double period;
-    uint32_t ncell;
-    // two-level grid (clustered seeds): a bin with more than kDenseBin seeds carries its own
-    // s x s x s sub-grid, s = 1 << ls; sub[b] = (first virtual cell of bin b) << 3 | ls, and
-    // vstart[] is the start table of the virtual cells (x fastest inside a bin)
-    int two_level;
-    uint32_t nvirt;
-};
-constexpr uint32_t kDenseBin = 32;   // a uniform (Poisson, 8 per bin) input never reaches it
-constexpr uint32_t kSubPpc = 8;      // sub-grid sized for <= kSubPpc seeds per virtual cell
-constexpr int kMaxSubLog = 5;        // s <= 32
-constexpr int kSmallPeriodicGrid = 12; // periodic grids with fewer bins per axis take the two-level walk
-constexpr int kWlocRingNear = 3;     // bins of dilation of the two local weight bounds (Laguerre)
-constexpr int kWlocRingFar = 8;
-
-// One seed in grid order: 32 bytes, read with two 16-byte loads.
-struct __align__(16) Seed {
-    double x, y, z, w;
-};
-
-__host__ __device__ inline int clampi(int v, int lo, int hi) {
-    return v < lo ? lo : (v > hi ? hi : v);
-}
-
 __device__ inline void cell_coords(const GridDesc& G, double x, double y, double z,
                                    int& ix, int& iy, int& iz) {
     ix = clampi(int(floor((x - G.lo[0]) * G.inv_w[0])), 0, G.g[0] - 1);
@@ -67,13 +36,6 @@ __device__ inline Seed load_seed(const Seed* p) {
     Seed s;
     s.x = a.x; s.y = a.y; s.z = b.x; s.w = b.y;
     return s;
-}
-
-// delaunay/periodic.h:104-113 + periodic.cpp:80-84: instance of a translation
-__host__ __device__ inline uint32_t translation_to_instance(int tx, int ty, int tz) {
-    int i = (tz + 1) + 3 * (ty + 1) + 9 * (tx + 1);
-    // reorder_instances: 13 -> 0, 0..12 -> 1..13, 14..26 unchanged
-    return uint32_t(i == 13 ? 0 : (i < 13 ? i + 1 : i));
 }
 
 // ---------------------------------------------------------------------------------
@@ -197,6 +159,9 @@ int compact_failed(Ctx* c, const uint32_t* qlist_in, uint32_t nq_in, uint32_t* q
 int lloyd_update(Ctx* c);
 int select_range(Ctx* c, uint32_t* qout, uint32_t* count_out_host);
 int reduce_events(Ctx* c);
+// tpc.cu
+bool tpc_applicable(const Ctx* c);
+int run_cells_tpc(Ctx* c, uint32_t nq, const uint32_t* qlist, int collect_events);
 // microbench.cu
 int microbench(Ctx* c, b200vor_peaks* out);
 

@@ -1,0 +1,115 @@
+// tpc.cu -- cells_tpc_kernel: the first-pass cell kernel, ONE THREAD PER CELL (32 independent
+// cells per warp).  The per-cell algorithm is tpc_cell.cuh (neighbour walk on the counting-sort
+// grid in sorted distance shells, fp32-filtered half-space clipping with the security radius,
+// fp64 orthoscheme integration); this file only lays the cells out in shared memory and launches.
+//
+// Shared-memory layout (BT threads per block, 992 bytes per thread): arrays of COLUMNS, element k
+// of thread t at index k * BT + t, so that the 32 lanes of a warp always hit 32 different banks
+// (16-byte vertex records: four conflict-free quarter-warp phases) whatever slot each lane is at.
+//   V    [NT][BT]       16 B   x, y, z (fp32) | plane triple + error exponent
+//   gid  [PC][BT]        4 B   neighbour id of the plane slot
+//   pool [POOLCAP][BT]   4 B   candidates of the current distance shell
+//   L    [LCAP][BT]      4 B   sort keys of the shell / plane triples of the conflict vertices of a cut
+// Cells the kernel cannot finish inside these capacities (or within two rings of bins) are flagged
+// OVERFLOW / UNCERTIFIED and re-done by the team kernel (fused.cu); nothing is silently accepted.
+#include "common.cuh"
+#include "tpc_cell.cuh"
+
+#include <stdlib.h>
+
+namespace b200vor {
+namespace {
+
+template <int BT, bool EV>
+__global__ void __launch_bounds__(BT) cells_tpc_kernel(tpc::Params P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    tpc::F4* V = reinterpret_cast<tpc::F4*>(smem_raw);
+    uint32_t* gid = reinterpret_cast<uint32_t*>(V + tpc::NT * BT);
+    uint32_t* pool = gid + tpc::PC * BT;
+    uint32_t* L = pool + tpc::POOLCAP * BT;
+    const uint32_t c = blockIdx.x * BT + threadIdx.x;
+    if(c >= P.nq) {
+        return;
+    }
+    tpc::Mem<BT> M;
+    M.V = V + threadIdx.x;
+    M.gid = gid + threadIdx.x;
+    M.pool = pool + threadIdx.x;
+    M.L = L + threadIdx.x;
+    tpc::compute_cell<BT, EV>(P, c, M);
+}
+
+constexpr size_t kBytesPerThread =
+    sizeof(tpc::F4) * tpc::NT + 4 * tpc::PC + 4 * tpc::POOLCAP + 4 * tpc::LCAP;
+
+template <int BT> int launch(Ctx* c, const tpc::Params& P, int collect_events) {
+    const size_t smem = kBytesPerThread * BT;
+    const uint32_t nblk = (P.nq + BT - 1) / BT;
+    if(collect_events) {
+        B200_CUDA_CHECK(cudaFuncSetAttribute(cells_tpc_kernel<BT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        cells_tpc_kernel<BT, true><<<nblk, BT, smem, c->stream>>>(P);
+    } else {
+        B200_CUDA_CHECK(cudaFuncSetAttribute(cells_tpc_kernel<BT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        cells_tpc_kernel<BT, false><<<nblk, BT, smem, c->stream>>>(P);
+    }
+    c->stats.gpu_launches++;
+    B200_CUDA_CHECK(cudaGetLastError());
+    return B200VOR_OK;
+}
+
+}  // namespace
+
+// can the thread-per-cell kernel take the cells of this context?  (unweighted, single-level grid,
+// at least a 3x3x3 block of bins on a periodic domain, ids that fit 27 bits)
+bool tpc_applicable(const Ctx* c) {
+    if(c->has_w || c->grid.two_level || c->n >= (1u << 27)) {
+        return false;
+    }
+    if(c->periodic) {
+        const int gmin = std::min(c->grid.g[0], std::min(c->grid.g[1], c->grid.g[2]));
+        if(gmin < 3) {
+            return false;
+        }
+    }
+    return true;
+}
+
+int run_cells_tpc(Ctx* c, uint32_t nq, const uint32_t* qlist, int collect_events) {
+    if(nq == 0) {
+        return B200VOR_OK;
+    }
+    tpc::Params P;
+    P.G = c->grid;
+    P.sorted = c->sorted.p;
+    P.cell_start = c->cell_start.p;
+    P.perm = c->perm.p;
+    P.n = c->n;
+    P.periodic = c->periodic;
+    P.period = c->periodic ? c->period : 0.0;
+    for(int a = 0; a < 6; ++a) {
+        P.box[a] = c->box[a];
+    }
+    P.nq = nq;
+    P.qlist = qlist;
+    P.m = c->m.p;
+    P.mg = c->mg.p;
+    P.status = c->status.p;
+    P.evcount = collect_events ? c->evcount.p : nullptr;
+    P.target = 20.f;
+    if(const char* e = getenv("B200VOR_TPC_TARGET")) {   // development knobs
+        P.target = float(atof(e));
+    }
+    int bt = 64;
+    if(const char* e = getenv("B200VOR_TPC_BT")) {
+        bt = atoi(e);
+    }
+    switch(bt) {
+        case 32: return launch<32>(c, P, collect_events);
+        case 96: return launch<96>(c, P, collect_events);
+        case 128: return launch<128>(c, P, collect_events);
+        case 224: return launch<224>(c, P, collect_events);
+        default: return launch<64>(c, P, collect_events);
+    }
+}
+
+}  // namespace b200vor

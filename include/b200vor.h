@@ -76,10 +76,13 @@ typedef struct b200vor_cell_params {
     uint32_t kmax;        /* cap on k for the re-launches of uncertified cells (0 = 384)      */
     uint32_t want_faces;  /* 1: keep per-cell face lists (+ areas) for b200vor_get_faces;
                              2: also the cell vertices for b200vor_get_vertices               */
-    uint32_t mode;        /* 0 = fused grid walk (no kNN table); the cells it flags UNCERTIFIED /
-                                 OVERFLOW are re-done by the kNN-table pipeline
-                             1 = fused grid walk only (flags are left on the cells)
-                             2 = kNN table -> clipper (re-launch failing cells with larger k) */
+    uint32_t mode;        /* 0 = grid walk, no kNN table: thread-per-cell kernel first (when the input
+                                 allows it: no weights, no face lists, single-level grid), the cells
+                                 it flags UNCERTIFIED / OVERFLOW are re-done by the team kernel, then
+                                 by its large-cell instance, then by the kNN-table pipeline
+                             1 = team-kernel grid walk only (flags are left on the cells)
+                             2 = kNN table -> clipper (re-launch failing cells with larger k)
+                             3 = as 0 without the thread-per-cell kernel (team kernel first)       */
     uint32_t want_energy; /* 1: also integrate |x - p_i|^2 over every cell (CVT energy) for
                              b200vor_get_cvt                                               */
 } b200vor_cell_params;
@@ -99,7 +102,7 @@ typedef struct b200vor_stats {
     uint64_t sum_tets;               /* I: integration terms                              */
     uint64_t gpu_launches;           /* kernels launched by this context so far           */
     uint32_t grid_dim[3];
-    uint32_t reserved0;
+    uint32_t tpc_cells;              /* cells the thread-per-cell kernel was launched on (last call) */
     uint64_t sum_scans;              /* fused walk: distance-shell scans of the grid, summed over cells */
 } b200vor_stats;
 

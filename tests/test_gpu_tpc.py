@@ -1,0 +1,112 @@
+"""GPU parity of the thread-per-cell kernel (tpc.cu): the default first pass of
+b200vor_compute_cells / b200vor_lloyd when no face lists are requested.  Checked against the
+CPU oracle (volumes, centroids), against the team kernel on the same input (mode 3), and for
+the size-independent properties at a BASELINE-scale input."""
+import numpy as np
+import pytest
+
+import oracles
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def Context():
+    from geogram_b200 import Context as C
+    return C
+
+
+@pytest.mark.parametrize("periodic", [True, False])
+@pytest.mark.parametrize("n", [2000, 100000])
+def test_tpc_vs_oracle_and_team_kernel(Context, port, n, periodic):
+    xyz = oracles.uniform_seeds(n, 77 + n)
+    ctx = Context(0)
+    if periodic:
+        ctx.set_domain_periodic(1.0)
+    ctx.set_points(xyz)
+    ctx.compute_cells()                      # mode 0: thread-per-cell first
+    s = ctx.stats()
+    assert s["tpc_cells"] == n               # the new kernel really ran on every cell
+    m, mg, st = ctx.get_cells()
+    assert (st == 0).all(), np.bincount(st)
+    O = port.cells(xyz, periodic=periodic)
+    assert np.all(np.abs(m - O.m) <= 1e-9 * O.m)
+    assert np.all(np.abs(mg - O.mg) <= 1e-9 * O.m[:, None])
+    assert abs(m.sum() - 1.0) < 1e-9
+    # event counters of the SURVEY 8(d) flop model are those of the reference algorithm
+    assert 0.8 * n * 14 < s["sum_planes"] < n * 60
+    # same cells as the team kernel
+    ctx.compute_cells(mode=3)
+    assert ctx.stats()["tpc_cells"] == 0
+    m3, mg3, st3 = ctx.get_cells()
+    assert (st3 == 0).all()
+    assert np.all(np.abs(m - m3) <= 1e-11 * m3)
+    assert np.all(np.abs(mg - mg3) <= 1e-11 * m3[:, None])
+
+
+def test_tpc_flagged_cells_are_redone(Context, port):
+    """Cells the thread-per-cell kernel cannot finish inside its capacities are handed to the
+    team kernel: every cell ends OK and the pass list shows the hand-over."""
+    n = 200000
+    xyz = oracles.uniform_seeds(n, 4242)
+    ctx = Context(0)
+    ctx.set_domain_periodic(1.0)
+    ctx.set_points(xyz)
+    ctx.compute_cells()
+    s = ctx.stats()
+    m, mg, st = ctx.get_cells()
+    assert (st == 0).all(), np.bincount(st)
+    assert s["passes"] >= 2 and s["n_pass"][0] == n and 0 < s["n_pass"][1] < 0.1 * n
+    assert abs(m.sum() - 1.0) < 1e-9
+    O = port.cells(xyz, periodic=True)
+    assert np.all(np.abs(m - O.m) <= 1e-9 * O.m)
+
+
+def test_tpc_lloyd_matches_team_kernel(Context):
+    n = 50000
+    xyz = oracles.uniform_seeds(n, 9)
+    a = Context(0)
+    a.set_domain_periodic(1.0)
+    a.set_points(xyz)
+    xa = a.lloyd(3)
+    b = Context(0)
+    b.set_domain_periodic(1.0)
+    b.set_points(xyz)
+    xb = b.lloyd(3, mode=3)
+    assert np.abs(xa - xb).max() < 1e-12
+
+
+def test_tpc_duplicates_and_small_sets(Context, port):
+    xyz = oracles.uniform_seeds(3000, 3)
+    xyz[10] = xyz[500]                       # exact duplicate: the higher index gets no cell
+    ctx = Context(0)
+    ctx.set_points(xyz)
+    ctx.compute_cells()
+    m, mg, st = ctx.get_cells()
+    assert st[500] & 32 and m[500] == 0.0 and st[10] == 0
+    assert abs(m.sum() - 1.0) < 1e-9
+    for n in (1, 2, 5, 40):
+        p = oracles.uniform_seeds(n, n)
+        ctx.set_points(p)
+        ctx.compute_cells()
+        m, mg, st = ctx.get_cells()
+        assert (st == 0).all() and abs(m.sum() - 1.0) < 1e-9
+
+
+def test_tpc_conservation_10m(Context):
+    """BASELINE configs[1] size: all cells certified, total volume conserved to 1e-9."""
+    import torch
+    n = 10000000
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(12345)
+    x = torch.rand((n, 3), dtype=torch.float64, device="cuda", generator=gen)
+    ctx = Context(0)
+    ctx.set_domain_periodic(1.0)
+    ctx.set_points_device(n, x.data_ptr())
+    ctx.compute_cells()
+    m = torch.empty((n,), dtype=torch.float64, device="cuda")
+    st = torch.empty((n,), dtype=torch.uint8, device="cuda")
+    ctx.get_cells_device(m.data_ptr(), None, st.data_ptr())
+    assert int((st != 0).sum().item()) == 0
+    assert abs(m.sum().item() - 1.0) < 1e-9
+    assert ctx.stats()["tpc_cells"] == n
