@@ -99,7 +99,7 @@ int run_cells_tpc(Ctx* c, uint32_t nq, const uint32_t* qlist, int collect_events
     if(const char* e = getenv("B200VOR_TPC_TARGET")) {   // development knobs
         P.target = float(atof(e));
     }
-    int bt = 64;
+    int bt = 224;
     if(const char* e = getenv("B200VOR_TPC_BT")) {
         bt = atoi(e);
     }
@@ -107,6 +107,8 @@ int run_cells_tpc(Ctx* c, uint32_t nq, const uint32_t* qlist, int collect_events
         case 32: return launch<32>(c, P, collect_events);
         case 96: return launch<96>(c, P, collect_events);
         case 128: return launch<128>(c, P, collect_events);
+        case 160: return launch<160>(c, P, collect_events);
+        case 192: return launch<192>(c, P, collect_events);
         case 224: return launch<224>(c, P, collect_events);
         default: return launch<64>(c, P, collect_events);
     }

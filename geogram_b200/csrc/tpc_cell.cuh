@@ -557,18 +557,28 @@ B200_HD inline void compute_cell(const Params& P, uint32_t c, const Mem<STRIDE>&
             M.ky(b) = ka;
         }
         // ================================================================ clip
-        for(uint32_t k = 0; k < cnt && !done; ++k) {
-            const uint32_t id = M.pl(k);
+        uint32_t k = 0;
+        while(!done) {
+          // ---- the next plane of the shell that cuts the cell.  Every thread advances through its
+          //      own pool here (cheap, regular work); the threads of a warp meet again at the cut
+          //      below, so that the expensive, irregular part runs with most lanes active ----
+          unsigned long long mask = 0ull;
+          uint32_t id = 0;
+          PlaneD pd = {0.0, 0.0, 0.0, 0.0, 0.0};
+          PlaneF pf = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          while(k < cnt && mask == 0ull) {
+            id = M.pl(k);
+            ++k;
             double d2;
-            const PlaneD pd = nbr_plane(P, F, id, d2);
+            pd = nbr_plane(P, F, id, d2);
             if(d2 > double(bnd)) {
                 continue;   // beyond the security radius (generic_RVD.h:2322): cannot cut
             }
-            const PlaneF pf = to_f(pd);
+            pf = to_f(pd);
             // ---- sign tests (triangle_is_in_conflict, convex_cell.cpp:870-969) in fp32:
             //      |s~ - s| <= n1 rho_v + 4.5u (n1 Rmax + |d|)
             const float K = 4.5f * kU * (pf.n1 * Rmax + pf.da) * (1.0f + 8.0f * kU);
-            unsigned long long mask = 0ull, unc = 0ull;
+            unsigned long long unc = 0ull;
             for(uint32_t s = 0; s < T; ++s) {
                 const F4 V = M.v(s);
                 const float val = fmaf(pf.a, V.x, fmaf(pf.b, V.y, fmaf(pf.c, V.z, pf.d)));
@@ -603,9 +613,11 @@ B200_HD inline void compute_cell(const Params& P, uint32_t c, const Mem<STRIDE>&
                     mask |= 1ull << s;
                 }
             }
-            if(mask == 0ull) {
-                continue;
-            }
+          }
+          if(mask == 0ull) {
+              break;   // shell used up
+          }
+          {
             // ================================================================ cut
             // (triangulate_conflict_zone, convex_cell.cpp:761-865, without adjacency)
             const uint32_t nconf = uint32_t(popc64(mask));
@@ -740,6 +752,7 @@ B200_HD inline void compute_cell(const Params& P, uint32_t c, const Mem<STRIDE>&
                 Rmax = sqrtf(R2) * (1.0f + 4.0f * kU);
                 bnd = 4.1f * R2;
             }
+          }
         }
         lo = hi;
     }

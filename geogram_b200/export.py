@@ -97,6 +97,49 @@ def save_cells_obj(path, nverts, vert_xyz, vert_faces, nfaces, m, mg, shrink=0.1
     return v_off - 1, nfac
 
 
+def save_cell_obj(nv, xyz, faces, nf, v_offset=1, shrink=0.0, g=None):
+    """The OBJ text ConvexCell::save (voronoi/convex_cell.cpp:282-352) writes for the cell once it is
+    re-hydrated into a VBW::ConvexCell the way the geogram plugin does it (dual triangle t = cell
+    vertex t, created in order; local vertex 1 + lv = face lv): byte for byte --
+    * triangles are pushed at the FRONT of the valid list (convex_cell.h:1143-1160), so the "v"
+      records come in reverse creation order;
+    * the loop of face v starts at the last listed triangle that touches v and follows
+      triangle_adjacent(t, (lv + 1) % 3), where the triangle across the edge opposite to local
+      vertex le owns the reversed directed edge (connect_triangles, convex_cell.cpp:1348-1411);
+    * numbers go through operator<< of a default ostream (6 significant digits, %g)."""
+    tri = [tuple(1 + int(x) for x in faces[t]) for t in range(nv)]
+    owner = {}
+    for t, (i, j, k) in enumerate(tri):
+        owner[(j, k)] = t
+        owner[(k, i)] = t
+        owner[(i, j)] = t
+    adj = [(owner[(k, j)], owner[(i, k)], owner[(j, i)]) for (i, j, k) in tri]
+    out = []
+    t_index = {}
+    v2t = {}
+    for pos, t in enumerate(range(nv - 1, -1, -1)):
+        p = np.asarray(xyz[t], np.float64)
+        if shrink != 0.0:
+            p = shrink * np.asarray(g) + (1.0 - shrink) * p
+        out.append("v %g %g %g\n" % (p[0], p[1], p[2]))
+        t_index[t] = pos
+        for v in tri[t]:
+            v2t[v] = t
+    for v in range(1, nf + 1):
+        if v not in v2t:
+            continue
+        line = "f "
+        t = v2t[v]
+        while True:
+            line += "%d " % (t_index[t] + v_offset)
+            lv = tri[t].index(v)
+            t = adj[t][(lv + 1) % 3]
+            if t == v2t[v]:
+                break
+        out.append(line + "\n")
+    return "".join(out)
+
+
 def delaunay_tets(nverts, vert_faces, nfaces, face_nbr, n):
     """Delaunay tetrahedra as an (nt, 4) uint32 array of vertex ids (periodic: real + n*instance, as
     PeriodicDelaunay3d numbers translated copies).  A tetrahedron is reported by the cell of its

@@ -17,7 +17,7 @@ def Context():
 
 
 @pytest.mark.parametrize("periodic", [True, False])
-@pytest.mark.parametrize("n", [2000, 100000])
+@pytest.mark.parametrize("n", [20000, 100000])
 def test_tpc_vs_oracle_and_team_kernel(Context, port, n, periodic):
     xyz = oracles.uniform_seeds(n, 77 + n)
     ctx = Context(0)

@@ -20,7 +20,7 @@ iters = []
 first = launches[order[0]] if order else None
 for lid in order:
     L = launches[lid]
-    if L["name"] == first["name"] and L["grid"] == first["grid"]:
+    if L["grid"] == first["grid"]:   # a full-size launch opens an iteration; re-launches are smaller
         iters.append({"grid": L["grid"], "kernel": L["name"], "warp_inst": 0.0, "thread_inst": 0.0,
                       "ns": 0.0, "dram_bytes": 0.0, "launches": 0})
     it = iters[-1]
