@@ -72,6 +72,7 @@ class Stats(ctypes.Structure):
         ("grid_dim", ctypes.c_uint32 * 3),
         ("tpc_cells", ctypes.c_uint32),
         ("sum_scans", ctypes.c_uint64),
+        ("exact_cells", ctypes.c_uint32), ("reserved1", ctypes.c_uint32),
     ]
 
     def as_dict(self):

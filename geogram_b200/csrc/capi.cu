@@ -19,6 +19,9 @@ void set_error(const char* fmt, ...) {
 
 namespace {
 
+// which kernel takes the first pass of mode 0 (measured: DESIGN.md section 9)
+constexpr bool kTpcFirstByDefault = false;
+
 __global__ void max_kernel(const double* __restrict__ w, uint32_t n, double* out) {
     __shared__ double sm[8];
     double mx = -1e300;
@@ -198,10 +201,14 @@ int cells_pipeline(Ctx* c, const b200vor_cell_params* params, bool collect_event
     memset(c->stats.k_pass, 0, sizeof(c->stats.k_pass));
     int pass0 = 0;
     c->stats.tpc_cells = 0;
-    if(p.mode == 0 && !p.want_faces && !p.want_energy && tpc_applicable(c)) {
+    const uint32_t nq0 = nq;
+    const uint32_t* const qlist0 = qlist;
+    c->stats.exact_cells = 0;
+    if((p.mode == 4 || (p.mode == 0 && kTpcFirstByDefault)) && p.want_faces <= 1 && !p.want_energy &&
+       tpc_applicable(c)) {
         // thread-per-cell kernel (tpc.cu): one launch; what it flags goes to the team kernel
         T.mark(2);
-        if((rc = run_cells_tpc(c, nq, qlist, collect_events ? 1 : 0))) {
+        if((rc = run_cells_tpc(c, nq, qlist, int(p.want_faces), collect_events ? 1 : 0, 0))) {
             return rc;
         }
         T.mark(0);
@@ -322,6 +329,31 @@ int cells_pipeline(Ctx* c, const b200vor_cell_params* params, bool collect_event
         qlist = out;
         nq = nfail;
         k = std::min(2 * k, p.kmax);
+    }
+    // ---- exact pass: cells a kernel flagged UNCERTAIN (a sign test inside the fp64 error bound:
+    //      degenerate input) are re-done by the large thread-per-cell instance, which decides such
+    //      ties with expansion arithmetic and the reference's default rule (convex_cell.cpp:905-911)
+    if(p.mode != 1 && p.mode != 2 && p.want_faces <= 1 && !p.want_energy && tpc_applicable(c)) {
+        if((rc = c->qlist3.reserve(nq0))) {
+            return rc;
+        }
+        uint32_t nunc = 0;
+        if((rc = compact_failed(c, qlist0, nq0, c->qlist3.p, nullptr, &nunc, B200VOR_CELL_UNCERTAIN))) {
+            return rc;
+        }
+        if(nunc > 0) {
+            T.mark(2);
+            if((rc = run_cells_tpc(c, nunc, c->qlist3.p, int(p.want_faces), collect_events ? 1 : 0, 1))) {
+                return rc;
+            }
+            T.mark(0);
+            c->stats.exact_cells = nunc;
+            if(c->stats.passes < 8) {
+                c->stats.n_pass[c->stats.passes] = nunc;
+                c->stats.k_pass[c->stats.passes] = 0;
+                c->stats.passes++;
+            }
+        }
     }
     T.mark(0);
     B200_CUDA_CHECK(cudaStreamSynchronize(c->stream));

@@ -161,7 +161,7 @@ int select_range(Ctx* c, uint32_t* qout, uint32_t* count_out_host);
 int reduce_events(Ctx* c);
 // tpc.cu
 bool tpc_applicable(const Ctx* c);
-int run_cells_tpc(Ctx* c, uint32_t nq, const uint32_t* qlist, int collect_events);
+int run_cells_tpc(Ctx* c, uint32_t nq, const uint32_t* qlist, int want_faces, int collect_events, int big);
 // microbench.cu
 int microbench(Ctx* c, b200vor_peaks* out);
 

@@ -1,0 +1,148 @@
+// exact_pred.cuh -- exact sign of the plane / cell-vertex test by floating-point expansions.
+//
+// The reference decides triangle_is_in_conflict exactly by default (use_exact_predicates_,
+// voronoi/convex_cell.cpp:137, :905-911: PCK::det_4d(p1, p2, p3, eqn) >= 0, filter
+// numerics/predicates/det4d.h:4-140, exact branch numerics/predicates.cpp:2073-2110 on
+// numerics/multi_precision.*).  Here the same decision is taken when the fp64 filter of the cell
+// kernels cannot certify a sign: the value of plane P at the vertex v = P0 ^ P1 ^ P2 is
+//     s = N / W,   W = det3[n0, n1, n2],
+//     N = d det3[n0, n1, n2] - d0 det3[n, n1, n2] - d1 det3[n, n2, n0] - d2 det3[n, n0, n1]
+// (the 4x4 determinant of the four plane equations developed along its last column), and both
+// N and W are evaluated EXACTLY as non-overlapping expansions (Shewchuk 1997: two-sum,
+// two-product by FMA, grow / scale with zero elimination), so sign(s) = sign(N) sign(W) is the
+// sign of the exact rational value of the fp64 inputs.  __host__ __device__: the host emulation
+// of the thread-per-cell kernel runs the same code.
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+
+#include "grid_types.h"
+
+namespace b200vor {
+namespace exact {
+
+B200_HD inline void two_sum(double a, double b, double& x, double& y) {
+    x = a + b;
+    const double bv = x - a;
+    const double av = x - bv;
+    y = (a - av) + (b - bv);
+}
+
+B200_HD inline void two_product(double a, double b, double& x, double& y) {
+    x = a * b;
+    y = fma(a, b, -x);
+}
+
+// h = b * e, zero components dropped; returns the length (<= 2 elen)
+B200_HD inline int scale_expansion(int elen, const double* e, double b, double* h) {
+    if(elen == 0) {
+        return 0;
+    }
+    int hlen = 0;
+    double Q, hh;
+    two_product(e[0], b, Q, hh);
+    if(hh != 0.0) {
+        h[hlen++] = hh;
+    }
+    for(int i = 1; i < elen; ++i) {
+        double p1, p0, sum;
+        two_product(e[i], b, p1, p0);
+        two_sum(Q, p0, sum, hh);
+        if(hh != 0.0) {
+            h[hlen++] = hh;
+        }
+        // fast two-sum (|p1| >= |sum| holds for non-overlapping e)
+        two_sum(p1, sum, Q, hh);
+        if(hh != 0.0) {
+            h[hlen++] = hh;
+        }
+    }
+    if(Q != 0.0) {
+        h[hlen++] = Q;
+    }
+    return hlen;
+}
+
+// h <- h + b in place (Shewchuk's grow-expansion with zero elimination): exact for any
+// non-overlapping h sorted by increasing magnitude; returns the new length (<= hlen + 1)
+B200_HD inline int grow_inplace(int hlen, double* h, double b) {
+    double Q = b;
+    int o = 0;
+    for(int i = 0; i < hlen; ++i) {
+        double s, err;
+        two_sum(Q, h[i], s, err);
+        if(err != 0.0) {
+            h[o++] = err;   // o <= i: the write never overtakes the read
+        }
+        Q = s;
+    }
+    if(Q != 0.0) {
+        h[o++] = Q;
+    }
+    return o;
+}
+
+// exact det3 of three fp64 rows as an expansion (<= 24 components)
+B200_HD inline int det3_expansion(const double* r0, const double* r1, const double* r2, double* acc /*[24]*/) {
+    // sum over the 6 permutations of  +/- r0[i] r1[j] r2[k]
+    const int perm[6][3] = {{0, 1, 2}, {1, 2, 0}, {2, 0, 1}, {0, 2, 1}, {1, 0, 2}, {2, 1, 0}};
+    int alen = 0;
+    for(int p = 0; p < 6; ++p) {
+        const double sgn = p < 3 ? 1.0 : -1.0;
+        double hi, lo, pe[2], term[4];
+        two_product(r0[perm[p][0]], r1[perm[p][1]], hi, lo);
+        int plen = 0;
+        if(lo != 0.0) {
+            pe[plen++] = lo;
+        }
+        if(hi != 0.0) {
+            pe[plen++] = hi;
+        }
+        const int tlen = scale_expansion(plen, pe, sgn * r2[perm[p][2]], term);
+        for(int i = 0; i < tlen; ++i) {
+            alen = grow_inplace(alen, acc, term[i]);
+        }
+    }
+    return alen;
+}
+
+B200_HD inline int expansion_sign(int len, const double* e) {
+    // the last non-zero component carries the sign (components are non-overlapping, increasing)
+    for(int i = len - 1; i >= 0; --i) {
+        if(e[i] > 0.0) {
+            return 1;
+        }
+        if(e[i] < 0.0) {
+            return -1;
+        }
+    }
+    return 0;
+}
+
+// Exact sign of plane (a, b, c, d) at the intersection of the planes P0, P1, P2 (each 4 doubles:
+// normal, offset; the planes must meet in one point).  Returns -1, 0, +1; 2 if the three planes do
+// not meet in a point (W == 0 exactly).
+B200_HD inline int plane_vertex_sign(const double* P0, const double* P1, const double* P2, const double* P) {
+    double W[24], D[24], sc[48], acc[200];
+    const int wlen = det3_expansion(P0, P1, P2, W);
+    const int sw = expansion_sign(wlen, W);
+    if(sw == 0) {
+        return 2;
+    }
+    // N = d W - d0 det3[n, n1, n2] - d1 det3[n, n2, n0] - d2 det3[n, n0, n1]
+    int alen = scale_expansion(wlen, W, P[3], acc);
+    const double* rows[3][2] = {{P1, P2}, {P2, P0}, {P0, P1}};
+    const double ds[3] = {P0[3], P1[3], P2[3]};
+    for(int k = 0; k < 3; ++k) {
+        const int dlen = det3_expansion(P, rows[k][0], rows[k][1], D);
+        const int slen = scale_expansion(dlen, D, -ds[k], sc);
+        for(int i = 0; i < slen; ++i) {
+            alen = grow_inplace(alen, acc, sc[i]);
+        }
+    }
+    return expansion_sign(alen, acc) * sw;
+}
+
+}  // namespace exact
+}  // namespace b200vor

@@ -20,38 +20,32 @@
 namespace b200vor {
 namespace {
 
-template <int BT, bool EV>
+template <int BT, bool EV, bool FACES, int NT, int PC, int LC>
 __global__ void __launch_bounds__(BT) cells_tpc_kernel(tpc::Params P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     tpc::F4* V = reinterpret_cast<tpc::F4*>(smem_raw);
-    uint32_t* gid = reinterpret_cast<uint32_t*>(V + tpc::NT * BT);
-    uint32_t* pool = gid + tpc::PC * BT;
+    uint32_t* gid = reinterpret_cast<uint32_t*>(V + NT * BT);
+    uint32_t* pool = gid + PC * BT;
     uint32_t* L = pool + tpc::POOLCAP * BT;
-    const uint32_t c = blockIdx.x * BT + threadIdx.x;
-    if(c >= P.nq) {
-        return;
-    }
+    const uint32_t c = blockIdx.x * BT + threadIdx.x;   // lanes past the end idle through the warp-uniform loops
     tpc::Mem<BT> M;
     M.V = V + threadIdx.x;
     M.gid = gid + threadIdx.x;
     M.pool = pool + threadIdx.x;
     M.L = L + threadIdx.x;
-    tpc::compute_cell<BT, EV>(P, c, M);
+    tpc::compute_cell<BT, EV, FACES, NT, PC, LC>(P, c, M);
 }
 
-constexpr size_t kBytesPerThread =
-    sizeof(tpc::F4) * tpc::NT + 4 * tpc::PC + 4 * tpc::POOLCAP + 4 * tpc::LCAP;
-
-template <int BT> int launch(Ctx* c, const tpc::Params& P, int collect_events) {
-    const size_t smem = kBytesPerThread * BT;
+template <int BT, int NT, int PC, int LC> int launch(Ctx* c, const tpc::Params& P, int collect_events, int faces) {
+    constexpr size_t per_thread = sizeof(tpc::F4) * NT + 4 * PC + 4 * tpc::POOLCAP + 4 * LC;
+    const size_t smem = per_thread * BT;
     const uint32_t nblk = (P.nq + BT - 1) / BT;
-    if(collect_events) {
-        B200_CUDA_CHECK(cudaFuncSetAttribute(cells_tpc_kernel<BT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        cells_tpc_kernel<BT, true><<<nblk, BT, smem, c->stream>>>(P);
-    } else {
-        B200_CUDA_CHECK(cudaFuncSetAttribute(cells_tpc_kernel<BT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        cells_tpc_kernel<BT, false><<<nblk, BT, smem, c->stream>>>(P);
-    }
+    typedef void (*Kern)(tpc::Params);
+    static const Kern table[4] = {cells_tpc_kernel<BT, false, false, NT, PC, LC>, cells_tpc_kernel<BT, false, true, NT, PC, LC>,
+                                  cells_tpc_kernel<BT, true, false, NT, PC, LC>, cells_tpc_kernel<BT, true, true, NT, PC, LC>};
+    Kern k = table[(collect_events ? 2 : 0) | (faces ? 1 : 0)];
+    B200_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    k<<<nblk, BT, smem, c->stream>>>(P);
     c->stats.gpu_launches++;
     B200_CUDA_CHECK(cudaGetLastError());
     return B200VOR_OK;
@@ -74,7 +68,9 @@ bool tpc_applicable(const Ctx* c) {
     return true;
 }
 
-int run_cells_tpc(Ctx* c, uint32_t nq, const uint32_t* qlist, int collect_events) {
+// big = 1: the large instance (64 vertex / plane slots), used for the cells of degenerate inputs
+// that the other kernels flag UNCERTAIN: ties are decided exactly here (exact_pred.cuh)
+int run_cells_tpc(Ctx* c, uint32_t nq, const uint32_t* qlist, int want_faces, int collect_events, int big) {
     if(nq == 0) {
         return B200VOR_OK;
     }
@@ -95,22 +91,25 @@ int run_cells_tpc(Ctx* c, uint32_t nq, const uint32_t* qlist, int collect_events
     P.mg = c->mg.p;
     P.status = c->status.p;
     P.evcount = collect_events ? c->evcount.p : nullptr;
+    P.nfaces = c->nfaces.p;
+    P.face_nbr = c->face_nbr.p;
+    P.face_area = c->face_area.p;
+    P.fcap = c->fcap;
     P.target = 20.f;
     if(const char* e = getenv("B200VOR_TPC_TARGET")) {   // development knobs
         P.target = float(atof(e));
+    }
+    if(big) {
+        return launch<64, tpc::NT_BIG, tpc::PC_BIG, tpc::LC_BIG>(c, P, collect_events, want_faces);
     }
     int bt = 224;
     if(const char* e = getenv("B200VOR_TPC_BT")) {
         bt = atoi(e);
     }
     switch(bt) {
-        case 32: return launch<32>(c, P, collect_events);
-        case 96: return launch<96>(c, P, collect_events);
-        case 128: return launch<128>(c, P, collect_events);
-        case 160: return launch<160>(c, P, collect_events);
-        case 192: return launch<192>(c, P, collect_events);
-        case 224: return launch<224>(c, P, collect_events);
-        default: return launch<64>(c, P, collect_events);
+        case 96: return launch<96, tpc::NT_STD, tpc::PC_STD, tpc::LC_STD>(c, P, collect_events, want_faces);
+        case 192: return launch<192, tpc::NT_STD, tpc::PC_STD, tpc::LC_STD>(c, P, collect_events, want_faces);
+        default: return launch<224, tpc::NT_STD, tpc::PC_STD, tpc::LC_STD>(c, P, collect_events, want_faces);
     }
 }
 

@@ -34,20 +34,26 @@
 #include <string.h>
 
 #include "../../include/b200vor.h"
+#include "exact_pred.cuh"
 #include "grid_types.h"
 
 namespace b200vor {
 namespace tpc {
 
-constexpr int NT = 40;        // cell-vertex slots
-constexpr int PC = 40;        // plane slots (0..5 = clipping box)
+constexpr int NT_STD = 40;    // cell-vertex slots of the standard instance
+constexpr int PC_STD = 40;    // plane slots (0..5 = clipping box)
+constexpr int NT_BIG = 64;    // the large instance: cells of degenerate inputs re-done with exact ties
+constexpr int PC_BIG = 64;
 constexpr int POOLCAP = 32;   // candidates of one distance shell
-constexpr int LCAP = 16;      // conflict vertices of one cut (2 * LCAP >= POOLCAP: shared words)
+constexpr int LC_STD = 16;    // conflict vertices of one cut (2 * LC >= POOLCAP: the words also hold sort keys)
+constexpr int LC_BIG = 32;
 constexpr int kMaxRing = 2;
 constexpr float kU = 5.9604645e-8f;               // 2^-24
 constexpr double kEps = 1.1102230246251565e-16;   // 2^-53
 constexpr uint32_t kImg0 = 13u;                   // base-3 code of the zero translation
-constexpr unsigned long long kLiveInit = 0x3Full | ~((1ull << PC) - 1ull);
+B200_HD constexpr unsigned long long live_init(int pc) {
+    return 0x3Full | (pc < 64 ? ~((1ull << (pc & 63)) - 1ull) : 0ull);
+}
 
 struct Params {
     GridDesc G;
@@ -65,6 +71,11 @@ struct Params {
     uint8_t* status;
     uint32_t* evcount;
     float target;            // expected candidates per distance shell
+    // face lists (FACES instances): neighbour ids ascending, areas (convex_cell.cpp:1160-1191)
+    uint32_t* nfaces;
+    uint32_t* face_nbr;
+    double* face_area;
+    uint32_t fcap;
 };
 
 #if defined(TPC_HOST_STATS)
@@ -84,7 +95,7 @@ template <int STRIDE> struct Mem {
     F4* V;            // [NT]
     uint32_t* gid;    // [PC]     neighbour (grid-order index | image << 27) of the plane slot
     uint32_t* pool;   // [POOLCAP]
-    uint32_t* L;      // [LCAP]   plane triples of the conflict vertices of a cut; the same words hold
+    uint32_t* L;      // [LC]     plane triples of the conflict vertices of a cut; the same words hold
                       //          the 16-bit sort keys of a shell (two per word) while it is sorted
     B200_HD F4& v(uint32_t s) const { return V[s * STRIDE]; }
     B200_HD uint32_t& g(uint32_t p) const { return gid[p * STRIDE]; }
@@ -161,6 +172,20 @@ B200_HD inline uint32_t ldu(const uint32_t* p) {
 #endif
 }
 B200_HD inline float fmaxf3(float a, float b, float c) { return fmaxf(a, fmaxf(b, c)); }
+// warp-level predicates: the 32 cells of a warp run the loops of compute_cell() together, so
+// that they can be brought back in step before the expensive part of every round
+B200_HD inline bool warp_any(bool p) {
+#if defined(__CUDA_ARCH__)
+    return __any_sync(0xffffffffu, p) != 0;
+#else
+    return p;
+#endif
+}
+B200_HD inline void warp_sync() {
+#if defined(__CUDA_ARCH__)
+    __syncwarp();
+#endif
+}
 
 struct PlaneD {
     double a, b, c, d;
@@ -324,9 +349,29 @@ B200_HD inline double coverage2(const GridDesc& Gd, const Seed& s, int cx, int c
 }
 
 // ---------------------------------------------------------------------------- the cell
-template <int STRIDE, bool EV>
+// exact decision of a tie of the fp64 filter (out of line: rare, and it carries a large frame)
+#if defined(__CUDA_ARCH__)
+__device__ __noinline__
+#else
+inline
+#endif
+int exact_plane_vertex_sign(const PlaneD& P0, const PlaneD& P1, const PlaneD& P2, const PlaneD& Q) {
+    const double a0[4] = {P0.a, P0.b, P0.c, P0.d}, a1[4] = {P1.a, P1.b, P1.c, P1.d}, a2[4] = {P2.a, P2.b, P2.c, P2.d},
+                 q[4] = {Q.a, Q.b, Q.c, Q.d};
+    return exact::plane_vertex_sign(a0, a1, a2, q);
+}
+
+// EV: event counters of the SURVEY 8(d) flop model.  FACES: face lists + areas.  NT / PC: capacities.
+template <int STRIDE, bool EV, bool FACES, int NT, int PC, int LCAP>
 B200_HD inline void compute_cell(const Params& P, uint32_t c, const Mem<STRIDE>& M) {
+    constexpr unsigned long long kLiveInit = live_init(PC);
     const GridDesc& Gd = P.G;
+    // every lane of a warp goes through the (warp-uniform) loops below; a lane without a cell
+    // (tail of the launch) idles through them and writes nothing
+    const bool alive = c < P.nq;
+    if(!alive) {
+        c = 0;
+    }
     const uint32_t i = P.qlist ? ldu(P.qlist + c) : c;
     Frame F;
     F.si = ld_seed(P.sorted + i);
@@ -380,7 +425,7 @@ B200_HD inline void compute_cell(const Params& P, uint32_t c, const Mem<STRIDE>&
         rmax = kMaxRing;
     }
     bool certified = false;
-    bool done = rmax < 1;
+    bool done = rmax < 1 || !alive;
     double cov2 = done ? 0.0 : coverage2(Gd, si, cx, cy, cz, ring);
     double lo = 0.0, hi = 0.0;
     // shell width: the ball expected to hold `target` more seeds at the density of the 27 bins
@@ -405,9 +450,9 @@ B200_HD inline void compute_cell(const Params& P, uint32_t c, const Mem<STRIDE>&
         c3 = P.target * 0.2387324146378430f * vol / float(cnt27 > 0u ? cnt27 : 1u);
     }
 
-    while(!done) {
+    while(warp_any(!done)) {
         // ---- next distance shell [lo, hi) ----
-        for(;;) {
+        for(; !done;) {
             if(lo > double(bnd)) {
                 certified = true;
                 done = true;
@@ -431,14 +476,11 @@ B200_HD inline void compute_cell(const Params& P, uint32_t c, const Mem<STRIDE>&
             hi = fmin(hi, fmin(double(bnd) * (1.0 + 1e-6) + 1e-300, cov2));
             break;
         }
-        if(done) {
-            break;
-        }
         // ================================================================ scan
         // seeds of the (2 ring + 1)^3 block of bins with lo <= d2 < hi -> pool
         uint32_t cnt = 0;
         bool overflow = false;
-        {
+        if(!done) {
             const int R1 = 2 * ring + 1;
             const int nrows = R1 * R1;
             const double slack = 1e-9 * Gd.w[0];
@@ -533,7 +575,7 @@ B200_HD inline void compute_cell(const Params& P, uint32_t c, const Mem<STRIDE>&
                 }
             }
         }
-        if(EV) {
+        if(EV && !done) {
             ++nscan;
         }
         if(overflow) {
@@ -541,7 +583,7 @@ B200_HD inline void compute_cell(const Params& P, uint32_t c, const Mem<STRIDE>&
             TPC_REASON(0);
             status |= B200VOR_CELL_OVERFLOW;
             done = true;
-            break;
+            cnt = 0;
         }
         // ================================================================ sort (insertion, by key)
         for(uint32_t a = 1; a < cnt; ++a) {
@@ -558,15 +600,16 @@ B200_HD inline void compute_cell(const Params& P, uint32_t c, const Mem<STRIDE>&
         }
         // ================================================================ clip
         uint32_t k = 0;
-        while(!done) {
-          // ---- the next plane of the shell that cuts the cell.  Every thread advances through its
-          //      own pool here (cheap, regular work); the threads of a warp meet again at the cut
-          //      below, so that the expensive, irregular part runs with most lanes active ----
+        bool clip = !done;   // this lane still has planes of the shell to offer
+        while(warp_any(clip)) {
+          // ---- the next plane of the shell that cuts the cell.  Every lane advances through its
+          //      own pool here (cheap, regular work); the lanes of the warp are brought back in step
+          //      before the cut, so that the expensive, irregular part runs with most lanes active ----
           unsigned long long mask = 0ull;
           uint32_t id = 0;
           PlaneD pd = {0.0, 0.0, 0.0, 0.0, 0.0};
           PlaneF pf = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-          while(k < cnt && mask == 0ull) {
+          while(clip && k < cnt && mask == 0ull) {
             id = M.pl(k);
             ++k;
             double d2;
@@ -599,25 +642,34 @@ B200_HD inline void compute_cell(const Params& P, uint32_t c, const Mem<STRIDE>&
                 const uint32_t s = uint32_t(ctz64(unc));
                 unc &= unc - 1ull;
                 const uint32_t t = M.v(s).w;
-                const VertexD V = make_vertex_d(slot_plane<STRIDE>(P, F, M, t & 63u), slot_plane<STRIDE>(P, F, M, (t >> 6) & 63u),
-                                                slot_plane<STRIDE>(P, F, M, (t >> 12) & 63u));
+                const PlaneD Q0 = slot_plane<STRIDE>(P, F, M, t & 63u), Q1 = slot_plane<STRIDE>(P, F, M, (t >> 6) & 63u),
+                             Q2 = slot_plane<STRIDE>(P, F, M, (t >> 12) & 63u);
+                const VertexD V = make_vertex_d(Q0, Q1, Q2);
                 const double dot = fma(pd.a, V.x, fma(pd.b, V.y, fma(pd.c, V.z, pd.d * V.w)));
                 const float Mq = d2f_ru(fmax(fmax(fabs(pd.a), fabs(pd.b)), fmax(fabs(pd.c), fabs(pd.d)))) * 1.0001f;
                 const bool tie = V.degenerate || d2f_rd(fabs(dot)) <= Mq * V.e;
                 TPC_REASON(5);
                 if(tie) {
                     TPC_REASON(6);
-                    // a tie never cuts (reference fast mode, convex_cell.cpp:968) and flags the cell
-                    status |= B200VOR_CELL_UNCERTAIN;
+                    // inside the fp64 bound as well: decided EXACTLY (expansions), with the rule of the
+                    // reference's default mode -- a vertex ON the plane is in conflict
+                    // (convex_cell.cpp:905-911: det_4d >= 0)
+                    const int sg = exact_plane_vertex_sign(Q0, Q1, Q2, pd);
+                    if(sg == 2) {
+                        status |= B200VOR_CELL_UNCERTAIN;   // the three planes do not meet in a point
+                    } else if(sg <= 0) {
+                        mask |= 1ull << s;
+                    }
                 } else if(dot < 0.0) {
                     mask |= 1ull << s;
                 }
             }
           }
+          warp_sync();
           if(mask == 0ull) {
-              break;   // shell used up
+              clip = false;   // shell used up
           }
-          {
+          if(clip) do {
             // ================================================================ cut
             // (triangulate_conflict_zone, convex_cell.cpp:761-865, without adjacency)
             const uint32_t nconf = uint32_t(popc64(mask));
@@ -752,6 +804,9 @@ B200_HD inline void compute_cell(const Params& P, uint32_t c, const Mem<STRIDE>&
                 Rmax = sqrtf(R2) * (1.0f + 4.0f * kU);
                 bnd = 4.1f * R2;
             }
+          } while(false);
+          if(done) {
+              clip = false;
           }
         }
         lo = hi;
@@ -763,10 +818,19 @@ B200_HD inline void compute_cell(const Params& P, uint32_t c, const Mem<STRIDE>&
 
     // ------------------------------------------------------------------ integration (fp64)
     const bool dead = (status & (B200VOR_CELL_EMPTY | B200VOR_CELL_DUPLICATE)) != 0;
-    const bool failed = (status & (B200VOR_CELL_OVERFLOW | B200VOR_CELL_UNCERTIFIED)) != 0;
+    const bool failed = (status & (B200VOR_CELL_OVERFLOW | B200VOR_CELL_UNCERTIFIED)) != 0 || !alive;
     double m6 = 0.0, gx = 0.0, gy = 0.0, gz = 0.0;
     unsigned long long used = 0ull;
     bool degenerate = false;
+    // FACES: 6 x signed volume of the orthoschemes of every face, accumulated per plane slot in the
+    // (dead) coordinate words of the vertex records -- only the plane triples are read from here on
+    auto facc = [&](uint32_t p) -> double& { return *reinterpret_cast<double*>(&M.v(p).x); };
+    if(FACES) {
+        static_assert(PC <= NT, "face accumulators live in the vertex records");
+        for(uint32_t p = 0; p < uint32_t(PC); ++p) {
+            facc(p) = 0.0;
+        }
+    }
     if(!dead && !failed) {
         for(uint32_t s = 0; s < T; ++s) {
             const uint32_t t = M.v(s).w;
@@ -807,6 +871,11 @@ B200_HD inline void compute_cell(const Params& P, uint32_t c, const Mem<STRIDE>&
                 const double vf = sg * tf * (A[f][0] * g0 + A[f][1] * g1 + A[f][2] * g2);
                 const double va = -sg * ta * (A[a][0] * g0 + A[a][1] * g1 + A[a][2] * g2);
                 m6 += vf + va;
+                if(FACES) {
+                    const uint32_t pf_ = e == 0 ? p0 : (e == 1 ? p1 : p2), pa_ = e == 0 ? p1 : (e == 1 ? p2 : p0);
+                    facc(pf_) += vf;
+                    facc(pa_) += va;
+                }
                 // first moment: volume x (foot_face + foot_edge + vertex) / 4, foot_edge = vertex - t d
                 gx += vf * (A[f][0] + 2.0 * X - tf * dx) + va * (A[a][0] + 2.0 * X - ta * dx);
                 gy += vf * (A[f][1] + 2.0 * Y - tf * dy) + va * (A[a][1] + 2.0 * Y - ta * dy);
@@ -822,12 +891,65 @@ B200_HD inline void compute_cell(const Params& P, uint32_t c, const Mem<STRIDE>&
             status |= B200VOR_CELL_DEGENERATE;
         }
     }
+    if(!alive) {
+        return;
+    }
     const double mass = (dead || failed) ? 0.0 : m6 / 6.0;
     P.m[row] = mass;
     P.mg[3 * size_t(row)] = (dead || failed) ? 0.0 : gx / 24.0 + mass * si.x;
     P.mg[3 * size_t(row) + 1] = (dead || failed) ? 0.0 : gy / 24.0 + mass * si.y;
     P.mg[3 * size_t(row) + 2] = (dead || failed) ? 0.0 : gz / 24.0 + mass * si.z;
     P.status[row] = uint8_t(status);
+    if(FACES) {
+        // face list: ids of the contributing planes, ascending (ConvexCell::v_global_index; periodic
+        // images as real + n * instance, periodic.h:95-99), areas from the orthoschemes:
+        // area_f = (6 vol_f) / (2 h_f), h_f = distance seed - plane = -lam_f |n_f|
+        uint32_t nf = 0;
+        if(!dead && !failed) {
+            unsigned long long rest = used;
+            while(rest) {
+                const uint32_t p = uint32_t(ctz64(rest));
+                rest &= rest - 1ull;
+                uint32_t id;
+                if(p < 6u) {
+                    id = B200VOR_BOX_ID + p;
+                } else {
+                    const uint32_t g = M.g(p), im = g >> 27;
+                    const uint32_t inst = translation_to_instance(int(im % 3u) - 1, int((im / 3u) % 3u) - 1, int(im / 9u) - 1);
+                    id = ldu(P.perm + (g & 0x7FFFFFFu)) + inst * P.n;
+                }
+                // ids staged in the pool / conflict-list words (dead by now): entry nf
+                if(nf < uint32_t(POOLCAP)) {
+                    M.pl(nf) = id;
+                } else {
+                    M.l(nf - uint32_t(POOLCAP)) = id;
+                }
+                ++nf;
+            }
+            static_assert(PC <= POOLCAP + LCAP, "face ids are staged in the pool and conflict-list words");
+            auto fid = [&](uint32_t k) -> uint32_t { return k < uint32_t(POOLCAP) ? M.pl(k) : M.l(k - uint32_t(POOLCAP)); };
+            rest = used;
+            uint32_t k = 0;
+            while(rest) {
+                const uint32_t p = uint32_t(ctz64(rest));
+                rest &= rest - 1ull;
+                const uint32_t id = fid(k);
+                uint32_t rk = 0;
+                for(uint32_t q = 0; q < nf; ++q) {
+                    rk += fid(q) < id ? 1u : 0u;
+                }
+                if(rk < P.fcap) {
+                    const PlaneD Pp = slot_plane<STRIDE>(P, F, M, p);
+                    const double nn = sqrt(Pp.a * Pp.a + Pp.b * Pp.b + Pp.c * Pp.c);
+                    const double h2 = -2.0 * Pp.lam * nn;
+                    P.face_nbr[size_t(row) * P.fcap + rk] = id;
+                    P.face_area[size_t(row) * P.fcap + rk] = h2 != 0.0 ? fabs(facc(p) / h2) : 0.0;
+                }
+                ++k;
+            }
+        }
+        P.nfaces[row] = nf;
+    }
     if(EV) {
         const uint32_t cP = nP < 0xffffu ? nP : 0xffffu, cV = nV < 0xfffu ? nV : 0xfffu, cS = nscan < 15u ? nscan : 15u;
         P.evcount[2 * size_t(row)] = cP | (cV << 16) | (cS << 28);

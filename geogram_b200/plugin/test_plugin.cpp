@@ -128,13 +128,29 @@ int main(int argc, char** argv) {
         }
         dref->set_vertices(N, v.data());
         dgpu->set_vertices(N, v.data());
+        // same neighbourhoods: equal sizes and equal squared distances, rank by rank (the criterion of
+        // test_nn_search -- indices may differ where two neighbours are exactly equidistant)
         bool same = true;
+        index_t differing_ids = 0;
         GEO::vector<index_t> a, b;
+        auto sqd = [&](index_t i, index_t j) {
+            double s = 0.0;
+            for(int c = 0; c < 3; ++c) {
+                const double d = v[3 * size_t(i) + c] - v[3 * size_t(j) + c];
+                s += d * d;
+            }
+            return s;
+        };
         for(index_t i = 0; i < N; ++i) {
             dref->get_neighbors(i, a);
             dgpu->get_neighbors(i, b);
-            same = same && (a == b);
+            same = same && a.size() == b.size();
+            for(index_t k = 0; same && k < a.size(); ++k) {
+                same = same && sqd(i, a[k]) == sqd(i, b[k]);
+                differing_ids += (a[k] != b[k]);
+            }
         }
+        std::printf("info delaunay neighbour ids differing on exact ties: %u\n", unsigned(differing_ids));
         CHECK(same, "delaunay_neighbors_identical_to_NN");
         dgpu->get_neighbors(700, b);
         CHECK(b.empty(), "delaunay_duplicate_rule");
@@ -144,7 +160,11 @@ int main(int argc, char** argv) {
         g->enlarge_neighborhood(123, 47);
         dref->get_neighbors(123, a);
         dgpu->get_neighbors(123, b);
-        CHECK(a == b && a.size() == 47, "delaunay_enlarge_neighborhood");
+        bool enl = a.size() == b.size() && a.size() == 47;
+        for(index_t k = 0; enl && k < a.size(); ++k) {
+            enl = sqd(123, a[k]) == sqd(123, b[k]);
+        }
+        CHECK(enl, "delaunay_enlarge_neighborhood");
         CHECK(dgpu->nearest_vertex(&pts[30]) == 10, "delaunay_nearest_vertex");
     }
 

@@ -76,13 +76,16 @@ typedef struct b200vor_cell_params {
     uint32_t kmax;        /* cap on k for the re-launches of uncertified cells (0 = 384)      */
     uint32_t want_faces;  /* 1: keep per-cell face lists (+ areas) for b200vor_get_faces;
                              2: also the cell vertices for b200vor_get_vertices               */
-    uint32_t mode;        /* 0 = grid walk, no kNN table: thread-per-cell kernel first (when the input
-                                 allows it: no weights, no face lists, single-level grid), the cells
-                                 it flags UNCERTIFIED / OVERFLOW are re-done by the team kernel, then
-                                 by its large-cell instance, then by the kNN-table pipeline
+    uint32_t mode;        /* 0 = grid walk, no kNN table: the faster of the two first-pass kernels (team
+                                 kernel / thread-per-cell kernel; the latter needs an unweighted input on a
+                                 single-level grid), the cells it flags UNCERTIFIED / OVERFLOW are re-done
+                                 by the team kernel, its large-cell instance, then the kNN-table pipeline
                              1 = team-kernel grid walk only (flags are left on the cells)
                              2 = kNN table -> clipper (re-launch failing cells with larger k)
-                             3 = as 0 without the thread-per-cell kernel (team kernel first)       */
+                             3 = team kernel first (then as 0)
+                             4 = thread-per-cell kernel first (then as 0)
+                             In modes 0, 3 and 4 the cells a kernel flags UNCERTAIN (degenerate input)
+                             are re-done with exact sign decisions when the input allows it            */
     uint32_t want_energy; /* 1: also integrate |x - p_i|^2 over every cell (CVT energy) for
                              b200vor_get_cvt                                               */
 } b200vor_cell_params;
@@ -104,6 +107,8 @@ typedef struct b200vor_stats {
     uint32_t grid_dim[3];
     uint32_t tpc_cells;              /* cells the thread-per-cell kernel was launched on (last call) */
     uint64_t sum_scans;              /* fused walk: distance-shell scans of the grid, summed over cells */
+    uint32_t exact_cells;            /* cells re-done with exact (expansion) sign decisions (last call) */
+    uint32_t reserved1;
 } b200vor_stats;
 
 /* ---- life cycle ---- */

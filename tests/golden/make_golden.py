@@ -108,8 +108,30 @@ def delaunay_tets():
     print("delaunay_tets_box_3000.npz", t.shape)
 
 
+def lattice_points(k=12, cells=16):
+    """k^3 lattice with DYADIC coordinates (i + 1/2) / cells: every bisector coefficient is exact in
+    fp64 in any frame, so the exact-mode decisions of the reference and of the GPU path are decisions
+    about the same real numbers."""
+    g = (np.arange(k) + 0.5) / float(cells)
+    X, Y, Z = np.meshgrid(g, g, g, indexing="ij")
+    return np.ascontiguousarray(np.stack([X.ravel(), Y.ravel(), Z.ravel()], axis=1))
+
+
+def lattice():
+    """Degenerate input: a cubic lattice in the box [0, 0.75]^3, cells by the unmodified reference's
+    kNN + VBW::ConvexCell path in its DEFAULT exact mode (ties are conflicts, convex_cell.cpp:905-911):
+    26 faces per interior cell, 18 of them of zero area."""
+    R = oracles.Reference()
+    xyz = lattice_points()
+    box = np.array([0, 0, 0, 0.75, 0.75, 0.75])
+    B = R.cells_knn(xyz, box=box, exact=True, areas=True)
+    save_cells("cells_box_lattice_exact_1728.npz", xyz, B, box=box)
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "cvt":
+    if len(sys.argv) > 1 and sys.argv[1] == "lattice":
+        lattice()
+    elif len(sys.argv) > 1 and sys.argv[1] == "cvt":
         cvt_energy()
     elif len(sys.argv) > 1 and sys.argv[1] == "tets":
         delaunay_tets()
@@ -117,3 +139,4 @@ if __name__ == "__main__":
         main()
         cvt_energy()
         delaunay_tets()
+        lattice()

@@ -16,11 +16,30 @@ extern "C" {
 long tpc_reason[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 }
 
+#include "../../geogram_b200/csrc/exact_pred.cuh"
+
 using namespace b200vor;
+
+// exact sign of plane P at the vertex P0 ^ P1 ^ P2 (exact_pred.cuh), for the test against rational arithmetic
+extern "C" int tpc_exact_sign(const double* P0, const double* P1, const double* P2, const double* P) {
+    return exact::plane_vertex_sign(P0, P1, P2, P);
+}
+
+// big != 0: the large instance (64 vertex / plane slots); nfaces / face_nbr / face_area (fcap 64) may be null
+extern "C" int tpc_host_cells_ex(uint32_t n, const double* xyz, int periodic, double period, const double* box,
+                                 double ppc, float target, double* m, double* mg, uint8_t* status,
+                                 uint32_t* evcount, int big, uint32_t* nfaces, uint32_t* face_nbr, double* face_area);
 
 extern "C" int tpc_host_cells(uint32_t n, const double* xyz, int periodic, double period, const double* box,
                               double ppc, float target, double* m, double* mg, uint8_t* status,
                               uint32_t* evcount) {
+    return tpc_host_cells_ex(n, xyz, periodic, period, box, ppc, target, m, mg, status, evcount, 0, nullptr, nullptr,
+                             nullptr);
+}
+
+extern "C" int tpc_host_cells_ex(uint32_t n, const double* xyz, int periodic, double period, const double* box,
+                                 double ppc, float target, double* m, double* mg, uint8_t* status,
+                                 uint32_t* evcount, int big, uint32_t* nfaces, uint32_t* face_nbr, double* face_area) {
     GridDesc G;
     G.periodic = periodic;
     G.period = period;
@@ -110,11 +129,16 @@ extern "C" int tpc_host_cells(uint32_t n, const double* xyz, int periodic, doubl
     P.status = status;
     P.evcount = evcount;
     P.target = target > 0.f ? target : 20.f;
+    P.nfaces = nfaces;
+    P.face_nbr = face_nbr;
+    P.face_area = face_area;
+    P.fcap = 64;
+    const bool faces = nfaces != nullptr;
 #pragma omp parallel
     {
-        tpc::F4 V[tpc::NT];
-        uint32_t gid[tpc::PC], pool[tpc::POOLCAP];
-        uint32_t L[tpc::LCAP];
+        tpc::F4 V[tpc::NT_BIG];
+        uint32_t gid[tpc::PC_BIG], pool[tpc::POOLCAP];
+        uint32_t L[tpc::LC_BIG];
         tpc::Mem<1> M;
         M.V = V;
         M.gid = gid;
@@ -122,7 +146,17 @@ extern "C" int tpc_host_cells(uint32_t n, const double* xyz, int periodic, doubl
         M.L = L;
 #pragma omp for schedule(dynamic, 256)
         for(uint32_t c = 0; c < n; ++c) {
-            tpc::compute_cell<1, true>(P, c, M);
+            if(big) {
+                if(faces) {
+                    tpc::compute_cell<1, true, true, tpc::NT_BIG, tpc::PC_BIG, tpc::LC_BIG>(P, c, M);
+                } else {
+                    tpc::compute_cell<1, true, false, tpc::NT_BIG, tpc::PC_BIG, tpc::LC_BIG>(P, c, M);
+                }
+            } else if(faces) {
+                tpc::compute_cell<1, true, true, tpc::NT_STD, tpc::PC_STD, tpc::LC_STD>(P, c, M);
+            } else {
+                tpc::compute_cell<1, true, false, tpc::NT_STD, tpc::PC_STD, tpc::LC_STD>(P, c, M);
+            }
         }
     }
     return 0;

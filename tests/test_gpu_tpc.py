@@ -24,7 +24,7 @@ def test_tpc_vs_oracle_and_team_kernel(Context, port, n, periodic):
     if periodic:
         ctx.set_domain_periodic(1.0)
     ctx.set_points(xyz)
-    ctx.compute_cells()                      # mode 0: thread-per-cell first
+    ctx.compute_cells(mode=4)                # thread-per-cell kernel first
     s = ctx.stats()
     assert s["tpc_cells"] == n               # the new kernel really ran on every cell
     m, mg, st = ctx.get_cells()
@@ -52,7 +52,7 @@ def test_tpc_flagged_cells_are_redone(Context, port):
     ctx = Context(0)
     ctx.set_domain_periodic(1.0)
     ctx.set_points(xyz)
-    ctx.compute_cells()
+    ctx.compute_cells(mode=4)
     s = ctx.stats()
     m, mg, st = ctx.get_cells()
     assert (st == 0).all(), np.bincount(st)
@@ -68,7 +68,7 @@ def test_tpc_lloyd_matches_team_kernel(Context):
     a = Context(0)
     a.set_domain_periodic(1.0)
     a.set_points(xyz)
-    xa = a.lloyd(3)
+    xa = a.lloyd(3, mode=4)
     b = Context(0)
     b.set_domain_periodic(1.0)
     b.set_points(xyz)
@@ -81,14 +81,14 @@ def test_tpc_duplicates_and_small_sets(Context, port):
     xyz[10] = xyz[500]                       # exact duplicate: the higher index gets no cell
     ctx = Context(0)
     ctx.set_points(xyz)
-    ctx.compute_cells()
+    ctx.compute_cells(mode=4)
     m, mg, st = ctx.get_cells()
     assert st[500] & 32 and m[500] == 0.0 and st[10] == 0
     assert abs(m.sum() - 1.0) < 1e-9
     for n in (1, 2, 5, 40):
         p = oracles.uniform_seeds(n, n)
         ctx.set_points(p)
-        ctx.compute_cells()
+        ctx.compute_cells(mode=4)
         m, mg, st = ctx.get_cells()
         assert (st == 0).all() and abs(m.sum() - 1.0) < 1e-9
 
@@ -103,10 +103,55 @@ def test_tpc_conservation_10m(Context):
     ctx = Context(0)
     ctx.set_domain_periodic(1.0)
     ctx.set_points_device(n, x.data_ptr())
-    ctx.compute_cells()
+    ctx.compute_cells(mode=4)
     m = torch.empty((n,), dtype=torch.float64, device="cuda")
     st = torch.empty((n,), dtype=torch.uint8, device="cuda")
     ctx.get_cells_device(m.data_ptr(), None, st.data_ptr())
     assert int((st != 0).sum().item()) == 0
     assert abs(m.sum().item() - 1.0) < 1e-9
     assert ctx.stats()["tpc_cells"] == n
+
+
+@pytest.mark.parametrize("periodic", [True, False])
+def test_tpc_face_lists_vs_oracle(Context, port, periodic):
+    n = 100000
+    xyz = oracles.uniform_seeds(n, 31)
+    ctx = Context(0)
+    if periodic:
+        ctx.set_domain_periodic(1.0)
+    ctx.set_points(xyz)
+    ctx.compute_cells(mode=4, want_faces=True)
+    assert ctx.stats()["tpc_cells"] == n
+    m, mg, st = ctx.get_cells()
+    nf, fn, fa = ctx.get_faces()
+    assert (st == 0).all()
+    O = port.cells(xyz, periodic=periodic, areas=True)
+    col = np.arange(64)[None, :]
+    assert (nf == O.nfaces).all()
+    assert not ((fn != O.face_nbr) & (col < O.nfaces[:, None])).any()      # connectivity bit-exact
+    mask = col < O.nfaces[:, None]
+    assert np.abs(fa[mask] - O.face_area[mask]).max() < 1e-12
+    assert np.all(np.abs(m - O.m) <= 1e-9 * O.m)
+
+
+@pytest.mark.parametrize("mode", [0, 3, 4])
+def test_degenerate_lattice_resolved_exactly(Context, mode):
+    """A cubic lattice (every sign test of the far planes is an exact tie): whatever kernel runs
+    first, the flagged cells are re-done with exact sign decisions and the reference's default tie
+    rule (convex_cell.cpp:905-911) -- status 0 everywhere, face lists and volumes equal to the
+    fixture the unmodified reference produced in exact mode."""
+    from conftest import Golden
+    G = Golden("cells_box_lattice_exact_1728.npz")
+    ctx = Context(0)
+    ctx.set_domain_box([0, 0, 0, 0.75, 0.75, 0.75])
+    ctx.set_points(G.xyz)
+    ctx.compute_cells(mode=mode, want_faces=True)
+    s = ctx.stats()
+    m, mg, st = ctx.get_cells()
+    nf, fn, fa = ctx.get_faces()
+    assert (st == 0).all(), np.bincount(st)
+    assert s["exact_cells"] > 0 or mode == 4
+    assert (nf == G.nfaces).all() and (fn == G.face_nbr).all()
+    assert np.abs(m - G.m).max() < 1e-15
+    assert abs(m.sum() - 0.75 ** 3) < 1e-14
+    assert np.abs(fa - G.face_area).max() < 1e-14
