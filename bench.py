@@ -199,6 +199,29 @@ def extra_configs(torch, dev, ctx, xyz_relaxed, n, args):
         r["workload"] = "BASELINE configs[2]: semi-discrete OT solve, uniform target, start weights 0.25 h^2 U(0,1), epsilon 1e-3"
         res["configs2_otm_solve"] = r
     del w, m, st, grad
+    # ---- the public NearestNeighborSearch path: grid build + exact kNN, k = 21
+    #      (Delaunay_NearestNeighbors' default 20 + the point itself), HBM roofline of SURVEY 8(d):
+    #      (76 + 4k) algorithmic bytes per seed over (t_bin + t_knn) ----
+    if not args.no_knn:
+        k = 21
+        c3 = Context(dev.index)
+        c3.set_domain_box([0, 0, 0, 1, 1, 1])
+        xyz_raw = torch.rand((n, 3), dtype=torch.float64, device=dev, generator=gen)
+        nbr = torch.empty((n, k), dtype=torch.int32, device=dev)
+        c3.set_points_device(n, xyz_raw.data_ptr())
+        c3.knn_device(k, nbr.data_ptr())
+        c3.set_points_device(n, xyz_raw.data_ptr())
+        g_ms = c3.stats()["ms_grid"]
+        c3.knn_device(k, nbr.data_ptr())
+        s = c3.stats()
+        hbm_peak, _ = load_peaks()
+        bw = (76.0 + 4.0 * k) * n / ((g_ms + s["ms_knn"]) * 1e-3) / 1e9
+        res["knn_k21"] = {"workload": "grid build + exact kNN, k=21, %d uniform seeds in the unit box (ids only)" % n,
+                          "ms_grid": g_ms, "ms_knn": s["ms_knn"], "queries_per_s": n / ((g_ms + s["ms_knn"]) * 1e-3),
+                          "algorithmic_bytes_per_seed": 76.0 + 4.0 * k, "achieved_gbs": bw, "hbm_peak_gbs": hbm_peak,
+                          "frac": bw / hbm_peak}
+        c3.close()
+        del xyz_raw, nbr
     # ---- configs[3]: clustered Gaussian-mixture seeds in the unit box (security-radius retries,
     #      two-level grid), one cell pass ----
     nc = args.clustered
@@ -251,6 +274,7 @@ def main():
     ap.add_argument("--no-extra", action="store_true", help="skip the extra_configs sub-results")
     ap.add_argument("--no-otm", action="store_true", help="skip the OT solve of extra_configs")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
+    ap.add_argument("--no-knn", action="store_true", help="skip the kNN sub-result of extra_configs")
     ap.add_argument("--clustered", type=int, default=10000000, help="seeds of the configs[3] sub-result (0 = skip)")
     ap.add_argument("--k0", type=int, default=0)
     ap.add_argument("--mode", type=int, default=0)

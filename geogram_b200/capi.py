@@ -209,6 +209,11 @@ class Context(object):
         self._check(self.lib.b200vor_knn(self.h, int(k), _ptr(nbr), _ptr(d2), 0))
         return nbr, d2
 
+    def knn_device(self, k, nbr_ptr, d2_ptr=None):
+        """rows of k into device buffers (n*k uint32, optional n*k float64), raw device addresses"""
+        self._check(self.lib.b200vor_knn(self.h, int(k), _ptr(int(nbr_ptr)),
+                                         _ptr(int(d2_ptr)) if d2_ptr else None, 1))
+
     def knn_points(self, q, k):
         q = np.ascontiguousarray(q, np.float64)
         nq = q.shape[0]

@@ -22,15 +22,40 @@
 namespace b200vor {
 namespace exact {
 
+// Individually rounded operations.  On the device the compiler must NOT contract a product with
+// the sum it feeds (fma(a, b, c) is a different number than round(round(a b) + c), and the error
+// terms below are only exact for the latter): the _rn intrinsics are never contracted.
+B200_HD inline double add_rn(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dadd_rn(a, b);
+#else
+    return a + b;
+#endif
+}
+B200_HD inline double sub_rn(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dsub_rn(a, b);
+#else
+    return a - b;
+#endif
+}
+B200_HD inline double mul_rn(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dmul_rn(a, b);
+#else
+    return a * b;
+#endif
+}
+
 B200_HD inline void two_sum(double a, double b, double& x, double& y) {
-    x = a + b;
-    const double bv = x - a;
-    const double av = x - bv;
-    y = (a - av) + (b - bv);
+    x = add_rn(a, b);
+    const double bv = sub_rn(x, a);
+    const double av = sub_rn(x, bv);
+    y = add_rn(sub_rn(a, av), sub_rn(b, bv));
 }
 
 B200_HD inline void two_product(double a, double b, double& x, double& y) {
-    x = a * b;
+    x = mul_rn(a, b);
     y = fma(a, b, -x);
 }
 
@@ -89,7 +114,6 @@ B200_HD inline int det3_expansion(const double* r0, const double* r1, const doub
     const int perm[6][3] = {{0, 1, 2}, {1, 2, 0}, {2, 0, 1}, {0, 2, 1}, {1, 0, 2}, {2, 1, 0}};
     int alen = 0;
     for(int p = 0; p < 6; ++p) {
-        const double sgn = p < 3 ? 1.0 : -1.0;
         double hi, lo, pe[2], term[4];
         two_product(r0[perm[p][0]], r1[perm[p][1]], hi, lo);
         int plen = 0;
@@ -99,7 +123,7 @@ B200_HD inline int det3_expansion(const double* r0, const double* r1, const doub
         if(hi != 0.0) {
             pe[plen++] = hi;
         }
-        const int tlen = scale_expansion(plen, pe, sgn * r2[perm[p][2]], term);
+        const int tlen = scale_expansion(plen, pe, p < 3 ? r2[perm[p][2]] : -r2[perm[p][2]], term);
         for(int i = 0; i < tlen; ++i) {
             alen = grow_inplace(alen, acc, term[i]);
         }

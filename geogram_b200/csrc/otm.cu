@@ -292,6 +292,7 @@ __global__ void jacobi_kernel(uint32_t n, const double* __restrict__ r, const do
 
 struct Resid {
     double norm2, sumvol, maxrel, minvol;
+    uint32_t bad = 0;   // cells that are not OK / EMPTY, or rows wider than the ELL matrix
 };
 
 struct Work {
@@ -314,14 +315,36 @@ int host_sum(Ctx* c, const double* part, int count, double* out) {
     return B200VOR_OK;
 }
 
+// cells whose measure or Hessian row cannot be trusted: anything but OK / EMPTY, or more faces than
+// the ELL rows hold (their m is "best effort", otm_coef_kernel would truncate the row)
+__global__ void otm_check_kernel(uint32_t n, const uint8_t* __restrict__ status, const uint32_t* __restrict__ nfaces,
+                                 uint32_t* __restrict__ bad) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i < n) {
+        const uint32_t st = status[i] & ~uint32_t(B200VOR_CELL_EMPTY);
+        if(st != 0u || nfaces[i] > kFcap) {
+            atomicAdd(bad, 1u);
+        }
+    }
+}
+
 int residual(Ctx* c, Work& W, const double* nu, double nu_uniform, double* b, Resid* R) {
+    int rc;
+    if((rc = c->counter.reserve(4))) {
+        return rc;
+    }
+    B200_CUDA_CHECK(cudaMemsetAsync(c->counter.p, 0, sizeof(uint32_t), c->stream));
+    otm_check_kernel<<<(c->n + kNT - 1) / kNT, kNT, 0, c->stream>>>(c->n, c->status.p, c->nfaces.p, c->counter.p);
     otm_residual_kernel<<<kNB, kNT, 0, c->stream>>>(c->n, c->m.p, nu, nu_uniform, b, W.part.p);
-    c->stats.gpu_launches++;
+    c->stats.gpu_launches += 2;
+    uint32_t hbad = 0;
+    B200_CUDA_CHECK(cudaMemcpyAsync(&hbad, c->counter.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     double h[4 * kNB];
-    int rc = host_sum(c, W.part.p, 4 * kNB, h);
+    rc = host_sum(c, W.part.p, 4 * kNB, h);
     if(rc) {
         return rc;
     }
+    R->bad = hbad;
     R->norm2 = 0.0; R->sumvol = 0.0; R->maxrel = 0.0; R->minvol = 1e300;
     for(int k = 0; k < kNB; ++k) {
         R->norm2 += h[k];
@@ -465,6 +488,12 @@ int otm_newton(Ctx* c, const double* nu_in, double* w_io, const b200vor_otm_para
     if((rc = residual(c, W, nu, nu_uniform, W.b.p, &cur))) {
         return fail(rc);
     }
+    if(cur.bad) {
+        // never iterate on volumes that are only best effort (flagged cells) or on truncated rows
+        set_error("b200vor_otm_newton: %u cell(s) of the start weights are flagged (not OK / EMPTY) or have more "
+                  "than %u faces", cur.bad, kFcap);
+        return fail(B200VOR_ERR_CAPACITY);
+    }
     // smallest target measure
     double numin = nu_uniform;
     if(nu) {
@@ -546,7 +575,7 @@ int otm_newton(Ctx* c, const double* nu_in, double* w_io, const b200vor_otm_para
             if((rc = residual(c, W, nu, nu_uniform, W.q.p, &trial))) {
                 return fail(rc);
             }
-            if(trial.minvol >= eps0 && trial.norm2 <= (1.0 - 0.5 * alpha) * cur.norm2) {
+            if(trial.bad == 0 && trial.minvol >= eps0 && trial.norm2 <= (1.0 - 0.5 * alpha) * cur.norm2) {
                 accepted = true;
                 break;
             }

@@ -96,8 +96,12 @@ int run_cells_tpc(Ctx* c, uint32_t nq, const uint32_t* qlist, int want_faces, in
     P.face_area = c->face_area.p;
     P.fcap = c->fcap;
     P.target = 20.f;
+    P.lockstep = 0;
     if(const char* e = getenv("B200VOR_TPC_TARGET")) {   // development knobs
         P.target = float(atof(e));
+    }
+    if(const char* e = getenv("B200VOR_TPC_LOCKSTEP")) {
+        P.lockstep = atoi(e);
     }
     if(big) {
         return launch<64, tpc::NT_BIG, tpc::PC_BIG, tpc::LC_BIG>(c, P, collect_events, want_faces);

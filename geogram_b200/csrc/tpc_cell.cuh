@@ -71,6 +71,7 @@ struct Params {
     uint8_t* status;
     uint32_t* evcount;
     float target;            // expected candidates per distance shell
+    int lockstep;            // 1: the lanes of a warp offer their k-th plane together (A/B knob)
     // face lists (FACES instances): neighbour ids ascending, areas (convex_cell.cpp:1160-1191)
     uint32_t* nfaces;
     uint32_t* face_nbr;
@@ -552,8 +553,7 @@ B200_HD inline void compute_cell(const Params& P, uint32_t c, const Mem<STRIDE>&
                     const int sx = sp ? sx1 : 0;
                     const double ox = double(sx) * F.period;
                     const uint32_t im = uint32_t(sx + 1) + 3u * uint32_t(sy + 1) + 9u * uint32_t(sz + 1);
-                    for(uint32_t j = ja; j < ja + jn; ++j) {
-                        const Seed sj = ld_seed(P.sorted + j);
+                    auto consider = [&](const Seed& sj, uint32_t j) {
                         const double qx = (sj.x + ox) - si.x, qy = (sj.y + oy) - si.y, qz = (sj.z + oz) - si.z;
                         const double d2 = fma(qz, qz, fma(qy, qy, qx * qx));
                         if(d2 >= lo && d2 < hi && !(j == i && im == kImg0)) {
@@ -571,6 +571,21 @@ B200_HD inline void compute_cell(const Params& P, uint32_t c, const Mem<STRIDE>&
                                 overflow = true;
                             }
                         }
+                    };
+                    // four seeds per round: the loads are issued together (few warps per scheduler:
+                    // the latency of a lone load is not hidden by other warps)
+                    const uint32_t je = ja + jn;
+                    uint32_t j = ja;
+                    for(; j + 4u <= je; j += 4u) {
+                        const Seed s0 = ld_seed(P.sorted + j), s1 = ld_seed(P.sorted + j + 1u),
+                                   s2 = ld_seed(P.sorted + j + 2u), s3 = ld_seed(P.sorted + j + 3u);
+                        consider(s0, j);
+                        consider(s1, j + 1u);
+                        consider(s2, j + 2u);
+                        consider(s3, j + 3u);
+                    }
+                    for(; j < je; ++j) {
+                        consider(ld_seed(P.sorted + j), j);
                     }
                 }
             }
@@ -609,9 +624,11 @@ B200_HD inline void compute_cell(const Params& P, uint32_t c, const Mem<STRIDE>&
           uint32_t id = 0;
           PlaneD pd = {0.0, 0.0, 0.0, 0.0, 0.0};
           PlaneF pf = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-          while(clip && k < cnt && mask == 0ull) {
+          uint32_t tried = 0;
+          while(clip && k < cnt && mask == 0ull && !(P.lockstep && tried)) {
             id = M.pl(k);
             ++k;
+            ++tried;
             double d2;
             pd = nbr_plane(P, F, id, d2);
             if(d2 > double(bnd)) {
@@ -680,7 +697,7 @@ B200_HD inline void compute_cell(const Params& P, uint32_t c, const Mem<STRIDE>&
                 done = true;
                 break;
             }
-            if(nconf > uint32_t(LCAP)) {
+            if(nconf > uint32_t(LCAP) || 3u * nconf > 64u) {
                 TPC_REASON(1);
                 status |= B200VOR_CELL_OVERFLOW;
                 done = true;
@@ -715,10 +732,10 @@ B200_HD inline void compute_cell(const Params& P, uint32_t c, const Mem<STRIDE>&
             const uint32_t pn = uint32_t(ctz64(~live));
             live |= 1ull << pn;
             M.g(pn) = id;
-            unsigned long long holes = mask;
-            uint32_t Ttop = T, nnew = 0;
-            bool ovf = false;
-            for(uint32_t a = 0; a < nconf && !ovf; ++a) {
+            // ---- border edges: directed dual edges of the conflict vertices whose twin is not among
+            //      them (bit 3 a + e = edge e of conflict vertex a) ----
+            unsigned long long border = 0ull;
+            for(uint32_t a = 0; a < nconf; ++a) {
                 const uint32_t t = M.l(a);
                 const uint32_t pa = t & 63u, pb = (t >> 6) & 63u, pc = (t >> 12) & 63u;
                 // twins of the directed edges (pa->pb), (pb->pc), (pc->pa), as first | second << 6
@@ -732,33 +749,37 @@ B200_HD inline void compute_cell(const Params& P, uint32_t c, const Mem<STRIDE>&
                     f2 |= (r0 == tw2) | (r1 == tw2) | (r2 == tw2);
                 }
                 // (a vertex never holds the twin of its own edge: b == a needs no exclusion)
-                for(uint32_t e = 0; e < 3; ++e) {
-                    const bool interior = e == 0 ? f0 : (e == 1 ? f1 : f2);
-                    if(interior) {
-                        continue;
+                border |= (unsigned long long)((f0 ? 0u : 1u) | (f1 ? 0u : 2u) | (f2 ? 0u : 4u)) << (3u * a);
+            }
+            // ---- one new vertex (pn, u, v) per border edge (u -> v).  A separate loop over the set
+            //      bits: at step k every lane of the warp that has a k-th border edge is active ----
+            unsigned long long holes = mask;
+            uint32_t Ttop = T, nnew = 0;
+            bool ovf = false;
+            while(border) {
+                const uint32_t bit = uint32_t(ctz64(border));
+                border &= border - 1ull;
+                const uint32_t a = bit / 3u, e = bit - 3u * a;
+                const uint32_t t = M.l(a);
+                const uint32_t u = (t >> (6u * e)) & 63u, v = (t >> (6u * (e == 2u ? 0u : e + 1u))) & 63u;
+                uint32_t s;
+                if(holes) {
+                    s = uint32_t(ctz64(holes));
+                    holes &= holes - 1ull;
+                } else {
+                    s = Ttop++;
+                    if(s >= uint32_t(NT)) {
+                        ovf = true;
+                        break;
                     }
-                    // border edge (u -> v): one new vertex (pn, u, v)
-                    const uint32_t u = e == 0 ? pa : (e == 1 ? pb : pc);
-                    const uint32_t v = e == 0 ? pb : (e == 1 ? pc : pa);
-                    uint32_t s;
-                    if(holes) {
-                        s = uint32_t(ctz64(holes));
-                        holes &= holes - 1ull;
-                    } else {
-                        s = Ttop++;
-                        if(s >= uint32_t(NT)) {
-                            ovf = true;
-                            break;
-                        }
-                    }
-                    const PlaneF fu = to_f(slot_plane<STRIDE>(P, F, M, u));
-                    const PlaneF fv = to_f(slot_plane<STRIDE>(P, F, M, v));
-                    F4 V;
-                    const uint32_t code = make_vertex_f(pf, fu, fv, Rmax, V.x, V.y, V.z);
-                    V.w = pn | (u << 6) | (v << 12) | (code << 18);
-                    M.v(s) = V;
-                    ++nnew;
                 }
+                const PlaneF fu = to_f(slot_plane<STRIDE>(P, F, M, u));
+                const PlaneF fv = to_f(slot_plane<STRIDE>(P, F, M, v));
+                F4 V;
+                const uint32_t code = make_vertex_f(pf, fu, fv, Rmax, V.x, V.y, V.z);
+                V.w = pn | (u << 6) | (v << 12) | (code << 18);
+                M.v(s) = V;
+                ++nnew;
             }
             if(ovf) {
                 TPC_REASON(3);

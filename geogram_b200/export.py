@@ -140,10 +140,34 @@ def save_cell_obj(nv, xyz, faces, nf, v_offset=1, shrink=0.0, g=None):
     return "".join(out)
 
 
-def delaunay_tets(nverts, vert_faces, nfaces, face_nbr, n):
+def instance_translations():
+    """instance -> integer translation (delaunay/periodic.cpp:44-86 with reorder_instances):
+    instance 0 is the zero translation."""
+    T = np.zeros((27, 3), np.int64)
+    for tx in (-1, 0, 1):
+        for ty in (-1, 0, 1):
+            for tz in (-1, 0, 1):
+                i = (tz + 1) + 3 * (ty + 1) + 9 * (tx + 1)
+                T[0 if i == 13 else (i + 1 if i < 13 else i)] = (tx, ty, tz)
+    return T
+
+
+def _translation_to_instance(t):
+    """integer translations (..., 3) in {-1,0,1}^3 -> instance numbers (periodic.h:104-113)"""
+    i = (t[..., 2] + 1) + 3 * (t[..., 1] + 1) + 9 * (t[..., 0] + 1)
+    return np.where(i == 13, 0, np.where(i < 13, i + 1, i))
+
+
+def delaunay_tets(nverts, vert_faces, nfaces, face_nbr, n, xyz=None, period=0.0):
     """Delaunay tetrahedra as an (nt, 4) uint32 array of vertex ids (periodic: real + n*instance, as
     PeriodicDelaunay3d numbers translated copies).  A tetrahedron is reported by the cell of its
-    smallest real vertex index; vertices on the clipping box belong to no tetrahedron."""
+    smallest real vertex index (in the frame of that seed: the seed is instance 0); vertices on the
+    clipping box belong to no tetrahedron, so on a box domain the tetrahedra whose circumcentre the
+    box clipped away are missing.  Cells whose vertex list is not available (nverts == 0xFFFFFFFF:
+    finished by the kNN-table pipeline, or more than vcap vertices) contribute nothing: their number
+    is returned by `unavailable_cells`, and a caller that needs the complete triangulation must
+    check it.  With `xyz` (and `period` on a periodic domain) the tetrahedra are positively oriented
+    (orient3d > 0, the reference's convention, delaunay/delaunay.h:336-368)."""
     vcap = vert_faces.shape[1]
     ok = _available(nverts, vcap)
     idx = np.arange(vcap)[None, :]
@@ -156,12 +180,33 @@ def delaunay_tets(nverts, vert_faces, nfaces, face_nbr, n):
     nb = nb[interior]
     keep = (seed[:, None] < (nb % n)).all(axis=1)
     tets = np.concatenate([seed[keep][:, None], nb[keep]], axis=1)
+    if xyz is not None and len(tets):
+        T = instance_translations().astype(np.float64) * float(period)
+        P = np.asarray(xyz)[tets % n] + T[tets // n]
+        det = np.einsum("ij,ij->i", P[:, 1] - P[:, 0], np.cross(P[:, 2] - P[:, 0], P[:, 3] - P[:, 0]))
+        flip = det < 0
+        tets[flip, 2], tets[flip, 3] = tets[flip, 3].copy(), tets[flip, 2].copy()
     return tets.astype(np.uint32)
 
 
-def tet_adjacency(tets):
+def unavailable_cells(nverts, vcap=64):
+    """Number of cells without a vertex list (they are missing from delaunay_tets / save_cells_obj):
+    nverts == 0xFFFFFFFF (finished by the kNN-table pipeline) or more than vcap vertices."""
+    nverts = np.asarray(nverts)
+    return int(((nverts == NOT_AVAILABLE) | ((nverts != NOT_AVAILABLE) & (nverts > vcap))).sum())
+
+
+def tet_adjacency(tets, n=None):
     """adj[c, lf] = tetrahedron sharing with c the facet opposite to local vertex lf, or -1
-    (Delaunay::cell_adjacent).  Pure index work: facets are matched by their sorted vertex triples."""
+    (Delaunay::cell_adjacent, delaunay/delaunay.h:369-380).  Pure index work: facets are matched by
+    their sorted vertex triples.
+
+    Periodic domain (pass n = number of real seeds): a tetrahedron is written in the frame of the cell
+    that reported it, so the same facet carries different instance numbers in its two tetrahedra;
+    every facet is first brought to a canonical frame -- translated so that its smallest real vertex
+    (ties: smallest translation) is instance 0 -- and then matched.  A periodic triangulation has no
+    boundary: no entry is -1.  Box domain: -1 means convex hull OR a neighbour that delaunay_tets does
+    not export (circumcentre clipped away by the box)."""
     tets = np.asarray(tets, np.int64)
     nt = tets.shape[0]
     adj = np.full((nt, 4), -1, np.int64)
@@ -171,6 +216,17 @@ def tet_adjacency(tets):
     lf = np.tile(np.arange(4), nt)
     c = np.repeat(np.arange(nt), 4)
     faces = np.stack([np.delete(tets, k, axis=1) for k in range(4)], axis=1).reshape(-1, 3)
+    if n is not None:
+        T = instance_translations()
+        real, tr = faces % n, T[faces // n]                                  # (F,3), (F,3,3)
+        # anchor = lexicographically smallest (real, tx, ty, tz)
+        code = ((real * 3 + tr[..., 0] + 1) * 3 + tr[..., 1] + 1) * 3 + tr[..., 2] + 1
+        anchor = np.argmin(code, axis=1)
+        rel = tr - tr[np.arange(len(faces)), anchor][:, None, :]
+        bad = (np.abs(rel) > 1).any(axis=(1, 2))                              # not representable: left unmatched
+        rel = np.clip(rel, -1, 1)
+        faces = real + n * _translation_to_instance(rel)
+        faces[bad] = -1 - np.arange(int(bad.sum()))[:, None]                  # unique keys
     faces = np.sort(faces, axis=1)
     order = np.lexsort((faces[:, 2], faces[:, 1], faces[:, 0]))
     f = faces[order]

@@ -348,10 +348,17 @@ void ConvexCellBatch::save_cells(const std::string& filename, double shrink) con
     }
 }
 
-void ConvexCellBatch::delaunay_tetrahedra(std::vector<global_index_t>& tets) const {
+index_t ConvexCellBatch::delaunay_tetrahedra(std::vector<global_index_t>& tets) const {
     tets.clear();
     const index_t n = nb_cells();
+    index_t unavailable = 0;
     for(index_t c = 0; c < n; ++c) {
+        // no vertex list (cell finished by the kNN-table pipeline, or more than 64 vertices): its
+        // tetrahedra are missing from the result -- counted, never silently dropped
+        if(!nverts_.empty() && (nverts_[c] == 0xFFFFFFFFu || nverts_[c] > 64u)) {
+            ++unavailable;
+            continue;
+        }
         const index_t nt = nb_t(c);
         for(index_t t = 0; t < nt; ++t) {
             global_index_t v[3];
@@ -368,6 +375,7 @@ void ConvexCellBatch::delaunay_tetrahedra(std::vector<global_index_t>& tets) con
             }
         }
     }
+    return unavailable;
 }
 
 void ConvexCellBatch::compute_mg(index_t c, double& m, vec3& mg) const {
@@ -395,7 +403,22 @@ double ConvexCellBatch::total_volume() const {
     return s;
 }
 
-void ConvexCellBatch::tet_adjacency(const std::vector<global_index_t>& tets, std::vector<int64_t>& adjacent) {
+namespace {
+// integer translation of a periodic instance and back (delaunay/periodic.h:104-113, periodic.cpp:80-84)
+void instance_translation(uint32_t inst, int t[3]) {
+    const int i = inst == 0 ? 13 : (inst <= 13 ? int(inst) - 1 : int(inst));
+    t[0] = i / 9 - 1;
+    t[1] = (i / 3) % 3 - 1;
+    t[2] = i % 3 - 1;
+}
+uint32_t translation_instance(const int t[3]) {
+    const int i = (t[2] + 1) + 3 * (t[1] + 1) + 9 * (t[0] + 1);
+    return uint32_t(i == 13 ? 0 : (i < 13 ? i + 1 : i));
+}
+}  // namespace
+
+void ConvexCellBatch::tet_adjacency(const std::vector<global_index_t>& tets, std::vector<int64_t>& adjacent,
+                                    index_t nb_real_vertices) {
     const size_t nt = tets.size() / 4;
     adjacent.assign(4 * nt, -1);
     struct Facet {
@@ -410,6 +433,34 @@ void ConvexCellBatch::tet_adjacency(const std::vector<global_index_t>& tets, std
             for(uint32_t lv = 0; lv < 4; ++lv) {
                 if(lv != lf) {
                     f.v[k++] = tets[4 * c + lv];
+                }
+            }
+            if(nb_real_vertices != 0) {
+                // periodic: the same facet carries different instance numbers in the frames of its two
+                // tetrahedra; bring it to the frame where its smallest (real, translation) vertex is
+                // instance 0
+                const index_t n = nb_real_vertices;
+                int tr[3][3];
+                int anchor = 0;
+                for(int a = 0; a < 3; ++a) {
+                    instance_translation(f.v[a] / n, tr[a]);
+                    const global_index_t ra = f.v[a] % n, r0 = f.v[anchor] % n;
+                    if(ra < r0 || (ra == r0 && std::lexicographical_compare(tr[a], tr[a] + 3, tr[anchor], tr[anchor] + 3))) {
+                        anchor = a;
+                    }
+                }
+                bool representable = true;
+                global_index_t canon[3];
+                for(int a = 0; a < 3; ++a) {
+                    int rel[3];
+                    for(int d = 0; d < 3; ++d) {
+                        rel[d] = tr[a][d] - tr[anchor][d];
+                        representable = representable && rel[d] >= -1 && rel[d] <= 1;
+                    }
+                    canon[a] = representable ? f.v[a] % n + n * translation_instance(rel) : 0;
+                }
+                if(representable) {
+                    f.v[0] = canon[0]; f.v[1] = canon[1]; f.v[2] = canon[2];
                 }
             }
             std::sort(f.v, f.v + 3);

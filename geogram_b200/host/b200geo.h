@@ -159,12 +159,19 @@ public:
     /* PeriodicDelaunay3d::save_cells (periodic_delaunay_3d.cpp:4363-4392): every cell, shrink 0.1 */
     void save_cells(const std::string& filename, double shrink = 0.1) const;
     /* Delaunay tetrahedra (Delaunay::cell_vertex, delaunay.h:336-485): 4 vertex ids each
-       (periodic: real + N*instance), every tetrahedron once */
-    void delaunay_tetrahedra(std::vector<global_index_t>& tets) const;
+       (periodic: real + N*instance, in the frame of the reporting cell), every tetrahedron once.
+       Box domain: tetrahedra whose circumcentre the box clipped away are not exported.
+       Returns the number of cells WITHOUT a vertex list (finished by the kNN-table pipeline, or
+       more than 64 vertices): their tetrahedra are missing, the caller must check for 0. */
+    index_t delaunay_tetrahedra(std::vector<global_index_t>& tets) const;
     /* Delaunay::cell_adjacent (delaunay.h:369-380) for a list of tetrahedra (4 ids each):
        adjacent[4 c + lf] = tetrahedron sharing the facet opposite to local vertex lf, or -1.
-       Pure host index work (facets matched by their sorted vertex triples). */
-    static void tet_adjacency(const std::vector<global_index_t>& tets, std::vector<int64_t>& adjacent);
+       Pure host index work (facets matched by their sorted vertex triples).  Periodic domain: pass
+       the number of real seeds; facets are matched in a canonical frame (smallest vertex = instance
+       0) and no entry is -1.  Box domain (nb_real_vertices = 0): -1 = convex hull, or a neighbour
+       that delaunay_tetrahedra does not export. */
+    static void tet_adjacency(const std::vector<global_index_t>& tets, std::vector<int64_t>& adjacent,
+                              index_t nb_real_vertices = 0);
 
 private:
     b200vor_ctx* ctx_;

@@ -129,6 +129,7 @@ extern "C" int tpc_host_cells_ex(uint32_t n, const double* xyz, int periodic, do
     P.status = status;
     P.evcount = evcount;
     P.target = target > 0.f ? target : 20.f;
+    P.lockstep = 0;
     P.nfaces = nfaces;
     P.face_nbr = face_nbr;
     P.face_area = face_area;

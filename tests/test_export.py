@@ -117,6 +117,19 @@ def test_export_geometry_on_gpu(tmp_path, periodic):
         r2 = ((c - P[0]) ** 2).sum()
         d2 = ((allp - c) ** 2).sum(axis=1)
         assert (d2 >= r2 * (1 - 1e-9)).all()             # empty circumsphere
+    # Delaunay::cell_adjacent on the EXPORTED tetrahedra; positive orientation
+    assert export.unavailable_cells(nv) == 0
+    tets = export.delaunay_tets(nv, vf, nf, fn, n, xyz=G.xyz, period=1.0 if periodic else 0.0)
+    P = G.xyz[tets % n] + T[tets // n]
+    det = np.einsum("ij,ij->i", P[:, 1] - P[:, 0], np.cross(P[:, 2] - P[:, 0], P[:, 3] - P[:, 0]))
+    assert (det > 0).all()
+    adj = export.tet_adjacency(tets, n if periodic else None)
+    c, lf = np.nonzero(adj >= 0)
+    assert ((adj[adj[c, lf]] == c[:, None]).sum(axis=1) == 1).all()           # symmetric
+    if periodic:
+        assert (adj >= 0).all()          # a periodic triangulation has no boundary
+    else:
+        assert (adj >= 0).mean() > 0.7   # -1 = hull, or a neighbour clipped away by the box
     # OBJ (ConvexCell::save format)
     path = os.path.join(str(tmp_path), "cells.obj")
     nvw, nfw = export.save_cells_obj(path, nv, vx, vf, nf, m, mg, shrink=0.1, cells=np.arange(0, n, 50))
