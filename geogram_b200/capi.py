@@ -29,7 +29,7 @@ EXPORTS = [
     "b200vor_knn", "b200vor_knn_points", "b200vor_compute_cells", "b200vor_get_cells",
     "b200vor_get_faces", "b200vor_get_vertices", "b200vor_get_cvt", "b200vor_otm_newton", "b200vor_get_spatial_order", "b200vor_lloyd", "b200vor_get_stats",
     "b200vor_set_points_per_cell", "b200vor_set_stream", "b200vor_set_query_range",
-    "b200vor_microbench",
+    "b200vor_microbench", "b200vor_selftest_exact_sign",
 ]
 
 
@@ -129,6 +129,7 @@ def load_library():
     lib.b200vor_set_stream.argtypes = [vp, vp]
     lib.b200vor_set_query_range.argtypes = [vp, u32, u32]
     lib.b200vor_microbench.argtypes = [vp, ctypes.POINTER(Peaks)]
+    lib.b200vor_selftest_exact_sign.argtypes = [vp, u32, vp, vp]
     _lib = lib
     return lib
 
@@ -296,6 +297,13 @@ class Context(object):
         self._check(self.lib.b200vor_lloyd(
             self.h, int(iters), ctypes.byref(p),
             _ptr(int(xyz_out_ptr)) if xyz_out_ptr else None, 1))
+
+    def exact_signs(self, planes):
+        """planes: (n, 4, 4) float64 -- rows P0, P1, P2, P; returns the exact signs computed on the device"""
+        planes = np.ascontiguousarray(planes, np.float64)
+        out = np.zeros(planes.shape[0], np.int32)
+        self._check(self.lib.b200vor_selftest_exact_sign(self.h, planes.shape[0], _ptr(planes), _ptr(out)))
+        return out
 
     def microbench(self):
         """Measured FP64 / FP32 FMA throughput and the issue-slot peak of this GPU (dict)."""

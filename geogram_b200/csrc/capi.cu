@@ -483,6 +483,11 @@ int b200vor_set_domain_periodic(b200vor_ctx* h, double period) {
         set_error("b200vor_set_domain_periodic: invalid argument");
         return B200VOR_ERR_ARG;
     }
+    if(uint64_t(h->c.n) * 27ull >= 0xFFFFFFF0ull) {
+        // the points were set first: the same check as in b200vor_set_points
+        set_error("b200vor_set_domain_periodic: n too large for 32-bit periodic ids");
+        return B200VOR_ERR_ARG;
+    }
     h->c.periodic = 1;
     h->c.period = period;
     h->c.cells_valid = h->c.faces_valid = false;
@@ -603,14 +608,13 @@ int b200vor_knn(b200vor_ctx* h, uint32_t k, uint32_t* nbr, double* d2, int on_de
         dn = c->out_nbr.p;
         dd = d2 ? c->out_d2.p : nullptr;
     }
-    if(c->grid_dirty && (rc = ensure_grid(c))) {
-        return rc;
-    }
     // the public kNN is not offered on a periodic domain (the reference's kd-tree has none)
-    int saved = c->grid.periodic;
-    if(saved) {
+    if(c->periodic) {
         set_error("b200vor_knn: not available on a periodic domain");
         return B200VOR_ERR_ARG;
+    }
+    if((c->grid_dirty || c->grid.periodic != c->periodic) && (rc = ensure_grid(c))) {
+        return rc;   // the domain changed after set_points: the grid is rebuilt for the current one
     }
     Timer T(c->stream);
     T.mark(1);
@@ -641,13 +645,13 @@ int b200vor_knn_points(b200vor_ctx* h, uint32_t nq, const double* q, uint32_t k,
         set_error("b200vor_knn_points: k=%u exceeds the number of points (%u)", k, c->n);
         return B200VOR_ERR_ARG;
     }
-    if(c->grid.periodic) {
+    if(c->periodic) {
         set_error("b200vor_knn_points: not available on a periodic domain");
         return B200VOR_ERR_ARG;
     }
     B200_CUDA_CHECK(cudaSetDevice(c->device));
     int rc;
-    if(c->grid_dirty && (rc = ensure_grid(c))) {
+    if((c->grid_dirty || c->grid.periodic != c->periodic) && (rc = ensure_grid(c))) {
         return rc;
     }
     uint32_t* dn = nbr;
@@ -889,6 +893,15 @@ int b200vor_get_spatial_order(b200vor_ctx* h, uint32_t* order, int on_device) {
     }
     B200_CUDA_CHECK(cudaStreamSynchronize(c->stream));
     return B200VOR_OK;
+}
+
+int b200vor_selftest_exact_sign(b200vor_ctx* h, uint32_t n, const double* planes, int* signs) {
+    if(!h || !planes || !signs || n == 0) {
+        set_error("b200vor_selftest_exact_sign: invalid argument");
+        return B200VOR_ERR_ARG;
+    }
+    B200_CUDA_CHECK(cudaSetDevice(h->c.device));
+    return exact_sign_selftest(&h->c, n, planes, signs);
 }
 
 int b200vor_microbench(b200vor_ctx* h, b200vor_peaks* peaks) {

@@ -782,10 +782,11 @@ __global__ void lloyd_kernel(uint32_t n, uint32_t u0, double* __restrict__ xyz,
         return;
     }
     double mm = m[i];
-    if(mm > 1e-30) {   // voronoi/CVT.cpp:154-163
+    if(mm > 1e-30) {   // voronoi/CVT.cpp:154-163: s = 1 / m, p = s * mg (same rounding as the reference)
+        const double s = 1.0 / mm;
 #pragma unroll
         for(int a = 0; a < 3; ++a) {
-            double x = mg[3 * size_t(i) + a] / mm;
+            double x = s * mg[3 * size_t(i) + a];
             if(periodic) {   // demo_Delaunay3d/main.cpp:443-451
                 if(x < 0.0) {
                     x += period;

@@ -162,6 +162,7 @@ int reduce_events(Ctx* c);
 // tpc.cu
 bool tpc_applicable(const Ctx* c);
 int run_cells_tpc(Ctx* c, uint32_t nq, const uint32_t* qlist, int want_faces, int collect_events, int big);
+int exact_sign_selftest(Ctx* c, uint32_t n, const double* planes_host, int* out_host);
 // microbench.cu
 int microbench(Ctx* c, b200vor_peaks* out);
 

@@ -108,26 +108,42 @@ B200_HD inline int grow_inplace(int hlen, double* h, double b) {
     return o;
 }
 
-// exact det3 of three fp64 rows as an expansion (<= 24 components)
-B200_HD inline int det3_expansion(const double* r0, const double* r1, const double* r2, double* acc /*[24]*/) {
-    // sum over the 6 permutations of  +/- r0[i] r1[j] r2[k]
-    const int perm[6][3] = {{0, 1, 2}, {1, 2, 0}, {2, 0, 1}, {0, 2, 1}, {1, 0, 2}, {2, 1, 0}};
-    int alen = 0;
-    for(int p = 0; p < 6; ++p) {
-        double hi, lo, pe[2], term[4];
-        two_product(r0[perm[p][0]], r1[perm[p][1]], hi, lo);
-        int plen = 0;
-        if(lo != 0.0) {
-            pe[plen++] = lo;
-        }
-        if(hi != 0.0) {
-            pe[plen++] = hi;
-        }
-        const int tlen = scale_expansion(plen, pe, p < 3 ? r2[perm[p][2]] : -r2[perm[p][2]], term);
-        for(int i = 0; i < tlen; ++i) {
-            alen = grow_inplace(alen, acc, term[i]);
-        }
+// Scratch of one exact sign evaluation.  ONE object owned by the caller: with separate local
+// arrays in the (inlined) helpers, nvcc 12.9 overlaid `term` of add_triple_product on the live
+// accumulator of plane_vertex_sign (stack colouring of the merged allocas; the device returned wrong
+// signs while every helper called on its own was right) -- see DESIGN.md section 9.
+struct Scratch {
+    double W[24], D[24], sc[48], acc[200];
+    double pe[2], term[4];
+};
+
+// acc <- acc + a b c exactly (one of the six terms of a 3x3 determinant); returns the new length
+B200_HD inline int add_triple_product(Scratch& S, int alen, double* acc, double a, double b, double c) {
+    double hi, lo;
+    two_product(a, b, hi, lo);
+    int plen = 0;
+    if(lo != 0.0) {
+        S.pe[plen++] = lo;
     }
+    if(hi != 0.0) {
+        S.pe[plen++] = hi;
+    }
+    const int tlen = scale_expansion(plen, S.pe, c, S.term);
+    for(int i = 0; i < tlen; ++i) {
+        alen = grow_inplace(alen, acc, S.term[i]);
+    }
+    return alen;
+}
+
+// exact det3 of three fp64 rows as an expansion (<= 24 components), written out term by term
+B200_HD inline int det3_expansion(Scratch& S, const double* r0, const double* r1, const double* r2, double* acc /*[24]*/) {
+    int alen = 0;
+    alen = add_triple_product(S, alen, acc, r0[0], r1[1], r2[2]);
+    alen = add_triple_product(S, alen, acc, r0[1], r1[2], r2[0]);
+    alen = add_triple_product(S, alen, acc, r0[2], r1[0], r2[1]);
+    alen = add_triple_product(S, alen, acc, r0[0], r1[2], -r2[1]);
+    alen = add_triple_product(S, alen, acc, r0[1], r1[0], -r2[2]);
+    alen = add_triple_product(S, alen, acc, r0[2], r1[1], -r2[0]);
     return alen;
 }
 
@@ -144,28 +160,38 @@ B200_HD inline int expansion_sign(int len, const double* e) {
     return 0;
 }
 
+// S.acc <- S.acc - d det3[r0, r1, r2] exactly; returns the new length of S.acc
+B200_HD inline int sub_scaled_det3(Scratch& S, int alen, const double* r0, const double* r1, const double* r2, double d) {
+    const int dlen = det3_expansion(S, r0, r1, r2, S.D);
+    const int slen = scale_expansion(dlen, S.D, -d, S.sc);
+    for(int i = 0; i < slen; ++i) {
+        alen = grow_inplace(alen, S.acc, S.sc[i]);
+    }
+    return alen;
+}
+
 // Exact sign of plane (a, b, c, d) at the intersection of the planes P0, P1, P2 (each 4 doubles:
 // normal, offset; the planes must meet in one point).  Returns -1, 0, +1; 2 if the three planes do
 // not meet in a point (W == 0 exactly).
-B200_HD inline int plane_vertex_sign(const double* P0, const double* P1, const double* P2, const double* P) {
-    double W[24], D[24], sc[48], acc[200];
-    const int wlen = det3_expansion(P0, P1, P2, W);
-    const int sw = expansion_sign(wlen, W);
+#if defined(__CUDACC__)
+#define B200_EXACT_NOINLINE __noinline__
+#else
+#define B200_EXACT_NOINLINE
+#endif
+// (never inlined on the device: its scratch must not be coloured together with the caller's locals)
+B200_EXACT_NOINLINE B200_HD static int plane_vertex_sign(const double* P0, const double* P1, const double* P2, const double* P) {
+    Scratch S;
+    const int wlen = det3_expansion(S, P0, P1, P2, S.W);
+    const int sw = expansion_sign(wlen, S.W);
     if(sw == 0) {
         return 2;
     }
     // N = d W - d0 det3[n, n1, n2] - d1 det3[n, n2, n0] - d2 det3[n, n0, n1]
-    int alen = scale_expansion(wlen, W, P[3], acc);
-    const double* rows[3][2] = {{P1, P2}, {P2, P0}, {P0, P1}};
-    const double ds[3] = {P0[3], P1[3], P2[3]};
-    for(int k = 0; k < 3; ++k) {
-        const int dlen = det3_expansion(P, rows[k][0], rows[k][1], D);
-        const int slen = scale_expansion(dlen, D, -ds[k], sc);
-        for(int i = 0; i < slen; ++i) {
-            alen = grow_inplace(alen, acc, sc[i]);
-        }
-    }
-    return expansion_sign(alen, acc) * sw;
+    int alen = scale_expansion(wlen, S.W, P[3], S.acc);
+    alen = sub_scaled_det3(S, alen, P, P1, P2, P0[3]);
+    alen = sub_scaled_det3(S, alen, P, P2, P0, P1[3]);
+    alen = sub_scaled_det3(S, alen, P, P0, P1, P2[3]);
+    return expansion_sign(alen, S.acc) * sw;
 }
 
 }  // namespace exact

@@ -51,7 +51,30 @@ template <int BT, int NT, int PC, int LC> int launch(Ctx* c, const tpc::Params& 
     return B200VOR_OK;
 }
 
+__global__ void exact_sign_kernel(uint32_t n, const double* __restrict__ planes, int* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i < n) {
+        const double* p = planes + 16 * size_t(i);
+        out[i] = exact::plane_vertex_sign(p, p + 4, p + 8, p + 12);
+    }
+}
+
 }  // namespace
+
+// self-test hook of the exact predicate (tests/test_gpu_tpc.py): signs of n (P0, P1, P2, P) quadruples
+int exact_sign_selftest(Ctx* c, uint32_t n, const double* planes_host, int* out_host) {
+    int rc;
+    if((rc = c->out_d2.reserve(16 * size_t(n))) || (rc = c->out_nbr.reserve(n))) {
+        return rc;
+    }
+    B200_CUDA_CHECK(cudaMemcpyAsync(c->out_d2.p, planes_host, 16 * size_t(n) * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    exact_sign_kernel<<<(n + 63) / 64, 64, 0, c->stream>>>(n, c->out_d2.p, reinterpret_cast<int*>(c->out_nbr.p));
+    c->stats.gpu_launches++;
+    B200_CUDA_CHECK(cudaGetLastError());
+    B200_CUDA_CHECK(cudaMemcpyAsync(out_host, c->out_nbr.p, size_t(n) * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    B200_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return B200VOR_OK;
+}
 
 // can the thread-per-cell kernel take the cells of this context?  (unweighted, single-level grid,
 // at least a 3x3x3 block of bins on a periodic domain, ids that fit 27 bits)

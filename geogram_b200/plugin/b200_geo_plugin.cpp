@@ -1,5 +1,5 @@
 /* b200_geo_plugin.cpp -- see b200_geo_plugin.h.  Compiled against the reference's headers only as a
- * test target (oracle/Makefile: plugin); links libgeoref.so (unmodified geogram) and libb200vor.so. */
+ * test target (oracle/Makefile: plugin); links the unmodified geogram built under oracle/_ref and libb200vor.so. */
 #include "b200_geo_plugin.h"
 
 #include <geogram/basic/command_line.h>

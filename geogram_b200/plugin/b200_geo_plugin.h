@@ -5,9 +5,9 @@
  *
  * This is what a geogram maintainer adds: it compiles against the reference's
  * headers and links libgeogram; nothing in geogram changes.  In this repository it is built as a
- * TEST TARGET only (oracle/Makefile, target `plugin`, against /root/reference/src/lib and
- * oracle/_ref/libgeoref.so) and exercised by tests/test_gpu_plugin.py; the product library
- * (libb200vor.so) never links the reference.
+ * TEST TARGET only (oracle/Makefile, target `plugin`, against /root/reference/src/lib and the
+ * unmodified reference library built under oracle/_ref) and exercised by tests/test_gpu_plugin.py
+ * through tests/plugin/test_plugin.cpp; the product library (libb200vor.so) never links the reference.
  *
  *   GEO::NearestNeighborSearch_B200   "B200NN"   points/nn_search.h:69-257, registered as in
  *                                                 src/tests/test_nn_search/main.cpp:60-65

@@ -227,6 +227,12 @@ typedef struct b200vor_peaks {
     uint32_t sm_count, reserved;
 } b200vor_peaks;
 int b200vor_microbench(b200vor_ctx* ctx, b200vor_peaks* peaks);
+
+/* self-test of the device's exact sign predicate (what decides the ties of degenerate inputs, the
+ * role of PCK::det_4d's exact branch, numerics/predicates.cpp:2073-2110): for each of n quadruples of
+ * planes (16 doubles: P0, P1, P2, P, host memory) the sign of P at the point P0 ^ P1 ^ P2
+ * (-1, 0, +1; 2 = the three planes do not meet in one point) */
+int b200vor_selftest_exact_sign(b200vor_ctx* ctx, uint32_t n, const double* planes, int* signs);
 /* tuning knob: target points per grid cell (default 8.0); takes effect at the next set_points */
 int b200vor_set_points_per_cell(b200vor_ctx* ctx, double ppc);
 

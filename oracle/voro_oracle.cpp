@@ -798,7 +798,7 @@ int vo_lloyd_update(uint32_t n, const double* xyz, const double* m, const double
         for(int c = 0; c < 3; ++c) {
             double x = xyz[3 * size_t(i) + c];
             if(m[i] > 1e-30) {                       /* CVT.cpp:154-163 */
-                x = mg[3 * size_t(i) + c] / m[i];
+                x = (1.0 / m[i]) * mg[3 * size_t(i) + c];   /* s = 1/m; p = s*mg, CVT.cpp:156-159 */
             }
             if(periodic) {                           /* demo_Delaunay3d/main.cpp:443-451 */
                 if(x < 0.0) {

@@ -155,3 +155,42 @@ def test_degenerate_lattice_resolved_exactly(Context, mode):
     assert np.abs(m - G.m).max() < 1e-15
     assert abs(m.sum() - 0.75 ** 3) < 1e-14
     assert np.abs(fa - G.face_area).max() < 1e-14
+
+
+def test_exact_predicate_on_device_vs_rational_arithmetic(Context):
+    """The device's exact sign predicate (exact_pred.cuh through b200vor_selftest_exact_sign) against
+    python Fractions: random, nearly degenerate and exactly degenerate (dyadic) plane quadruples."""
+    from fractions import Fraction as Fr
+
+    def det3(a, b, c):
+        return a[0] * (b[1] * c[2] - b[2] * c[1]) - a[1] * (b[0] * c[2] - b[2] * c[0]) + a[2] * (b[0] * c[1] - b[1] * c[0])
+
+    def exact(Pl):
+        F = [[Fr(float(x)) for x in p] for p in Pl]
+        W = det3(F[0][:3], F[1][:3], F[2][:3])
+        if W == 0:
+            return 2
+        N = (F[3][3] * W - F[0][3] * det3(F[3][:3], F[1][:3], F[2][:3]) - F[1][3] * det3(F[3][:3], F[2][:3], F[0][:3])
+             - F[2][3] * det3(F[3][:3], F[0][:3], F[1][:3]))
+        return ((N > 0) - (N < 0)) * ((W > 0) - (W < 0))
+
+    rng = np.random.default_rng(3)
+    cases = []
+    for it in range(600):
+        Pl = rng.standard_normal((4, 4))
+        if it % 3 == 0:
+            v = np.linalg.solve(Pl[:3, :3], -Pl[:3, 3])
+            Pl[3, 3] = -(Pl[3, :3] @ v)
+        if it % 3 == 1:
+            Pl = np.round(Pl * 8) / 8
+            if abs(np.linalg.det(Pl[:3, :3])) < 1e-9:
+                continue
+            v = np.round(np.linalg.solve(Pl[:3, :3], -Pl[:3, 3]) * 64) / 64
+            for k in range(4):
+                Pl[k, 3] = -(Pl[k, :3] @ v)
+        cases.append(Pl)
+    cases = np.array(cases)
+    got = Context(0).exact_signs(cases)
+    want = np.array([exact(c) for c in cases])
+    assert (got == want).all()
+    assert (want == 0).sum() > 150

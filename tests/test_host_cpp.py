@@ -10,8 +10,15 @@ LIB = os.path.join(ROOT, "geogram_b200", "lib")
 
 
 def _build():
-    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "geogram_b200", "csrc")])
-    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "geogram_b200", "host")])
+    """(re)builds the libraries when the CUDA toolchain is here; a box without nvcc uses the
+    prebuilt ones that travel with the snapshot, and skips if there are none"""
+    import shutil
+    have_nvcc = shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc")
+    if have_nvcc:
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "geogram_b200", "csrc")])
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "geogram_b200", "host")])
+    elif not (os.path.exists(os.path.join(LIB, "libb200vor.so")) and os.path.exists(os.path.join(LIB, "libb200geo.so"))):
+        pytest.skip("no CUDA toolkit and no prebuilt geogram_b200/lib/*.so")
 
 
 def test_host_library_exports_the_mirrored_interfaces():

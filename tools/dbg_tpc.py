@@ -28,3 +28,27 @@ for n in (1, 2, 5, 40, 3000):
     m, mg, st = ctx.get_cells()
     s = ctx.stats()
     print("n", n, "status", {int(v): int((st == v).sum()) for v in np.unique(st)}, "sum m - 1", m.sum() - 1.0, "passes", s["n_pass"][:s["passes"]], "grid", s["grid_dim"])
+
+# exact predicate on the device vs the host emulation library
+import ctypes
+lib = ctypes.CDLL(os.path.join(ROOT, "tests", "_build", "libtpc_host.so")) if os.path.exists(os.path.join(ROOT, "tests", "_build", "libtpc_host.so")) else None
+rng = np.random.default_rng(1)
+cases = []
+for it in range(600):
+    Pl = rng.standard_normal((4, 4))
+    if it % 3 == 0:
+        v = np.linalg.solve(Pl[:3, :3], -Pl[:3, 3]); Pl[3, 3] = -(Pl[3, :3] @ v)
+    if it % 3 == 1:
+        Pl = np.round(Pl * 8) / 8
+        if abs(np.linalg.det(Pl[:3, :3])) < 1e-9: continue
+        v = np.round(np.linalg.solve(Pl[:3, :3], -Pl[:3, 3]) * 64) / 64
+        for k in range(4): Pl[k, 3] = -(Pl[k, :3] @ v)
+    cases.append(Pl)
+cases = np.array(cases)
+ctx = Context(0)
+dev = ctx.exact_signs(cases)
+if lib is not None:
+    host = np.array([lib.tpc_exact_sign(*[np.ascontiguousarray(r).ctypes.data_as(ctypes.c_void_p) for r in c]) for c in cases])
+    print("exact sign device vs host: mismatches", int((dev != host).sum()), "of", len(cases), "zeros host", int((host == 0).sum()), "zeros dev", int((dev == 0).sum()))
+else:
+    print("dev signs hist", np.bincount(dev + 1))
