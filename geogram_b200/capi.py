@@ -30,7 +30,10 @@ EXPORTS = [
     "b200vor_get_faces", "b200vor_get_vertices", "b200vor_get_cvt", "b200vor_otm_newton", "b200vor_get_spatial_order", "b200vor_lloyd", "b200vor_get_stats",
     "b200vor_set_points_per_cell", "b200vor_set_stream", "b200vor_set_query_range",
     "b200vor_microbench", "b200vor_selftest_exact_sign",
+    "b200vor_comm_unique_id", "b200vor_comm_init", "b200vor_slab_set_halo_bins", "b200vor_slab_set_points",
+    "b200vor_slab_compute_cells", "b200vor_slab_lloyd", "b200vor_slab_get_stats",
 ]
+UNIQUE_ID_BYTES = 128
 
 
 class CellParams(ctypes.Structure):
@@ -83,6 +86,14 @@ class Stats(ctypes.Structure):
         return d
 
 
+class SlabStats(ctypes.Structure):
+    _fields_ = [("n_own", ctypes.c_uint32), ("n_ghost_x", ctypes.c_uint32), ("n_ghost_yz", ctypes.c_uint32),
+                ("n_local", ctypes.c_uint32), ("retries", ctypes.c_uint32), ("n_flagged", ctypes.c_uint32),
+                ("halo", ctypes.c_double), ("slab_lo", ctypes.c_double), ("slab_hi", ctypes.c_double),
+                ("ms_exchange", ctypes.c_float), ("ms_pack", ctypes.c_float), ("ms_grid", ctypes.c_float),
+                ("ms_clip", ctypes.c_float), ("bytes_sent", ctypes.c_uint64), ("bytes_received", ctypes.c_uint64)]
+
+
 class Peaks(ctypes.Structure):
     _fields_ = [("fp64_tflops", ctypes.c_double), ("fp32_tflops", ctypes.c_double),
                 ("issue_ginst_s", ctypes.c_double), ("sm_clock_mhz", ctypes.c_double),
@@ -130,6 +141,13 @@ def load_library():
     lib.b200vor_set_query_range.argtypes = [vp, u32, u32]
     lib.b200vor_microbench.argtypes = [vp, ctypes.POINTER(Peaks)]
     lib.b200vor_selftest_exact_sign.argtypes = [vp, u32, vp, vp]
+    lib.b200vor_comm_unique_id.argtypes = [vp]
+    lib.b200vor_comm_init.argtypes = [vp, vp, i32, i32]
+    lib.b200vor_slab_set_halo_bins.argtypes = [vp, dbl]
+    lib.b200vor_slab_set_points.argtypes = [vp, u32, ctypes.c_uint64, ctypes.c_uint64, vp, vp, i32]
+    lib.b200vor_slab_compute_cells.argtypes = [vp, ctypes.POINTER(CellParams)]
+    lib.b200vor_slab_lloyd.argtypes = [vp, u32, ctypes.POINTER(CellParams), vp, i32]
+    lib.b200vor_slab_get_stats.argtypes = [vp, ctypes.POINTER(SlabStats)]
     _lib = lib
     return lib
 
@@ -297,6 +315,57 @@ class Context(object):
         self._check(self.lib.b200vor_lloyd(
             self.h, int(iters), ctypes.byref(p),
             _ptr(int(xyz_out_ptr)) if xyz_out_ptr else None, 1))
+
+    # ---- multi-GPU slabs (include/b200vor.h, "x-slabs with halos"); one process per GPU ----
+    @staticmethod
+    def comm_unique_id():
+        """128 bytes (an ncclUniqueId) created by ONE rank; hand them to every rank"""
+        lib = load_library()
+        buf = ctypes.create_string_buffer(UNIQUE_ID_BYTES)
+        if lib.b200vor_comm_unique_id(buf) != 0:
+            raise B200VorError(lib.b200vor_last_error().decode("utf-8", "replace"))
+        return buf.raw
+
+    def comm_init(self, unique_id, rank, world):
+        buf = ctypes.create_string_buffer(bytes(unique_id), UNIQUE_ID_BYTES) if unique_id is not None else None
+        self._check(self.lib.b200vor_comm_init(self.h, buf, int(rank), int(world)))
+
+    def slab_set_halo_bins(self, bins):
+        self._check(self.lib.b200vor_slab_set_halo_bins(self.h, float(bins)))
+
+    def slab_set_points(self, xyz_own, first_global, n_total, w=None):
+        xyz_own = np.ascontiguousarray(xyz_own, np.float64)
+        if w is not None:
+            w = np.ascontiguousarray(w, np.float64)
+        self.n = xyz_own.shape[0]
+        self._check(self.lib.b200vor_slab_set_points(self.h, self.n, int(first_global), int(n_total),
+                                                     _ptr(xyz_own), _ptr(w), 0))
+
+    def slab_set_points_device(self, n_own, first_global, n_total, xyz_ptr, w_ptr=None):
+        self.n = int(n_own)
+        self._check(self.lib.b200vor_slab_set_points(self.h, self.n, int(first_global), int(n_total),
+                                                     _ptr(int(xyz_ptr)), _ptr(int(w_ptr)) if w_ptr else None, 1))
+
+    def slab_compute_cells(self, want_faces=False):
+        p = CellParams(0, 0, int(want_faces), 0, 0)
+        self._check(self.lib.b200vor_slab_compute_cells(self.h, ctypes.byref(p)))
+
+    def slab_lloyd(self, iters, out=None, want_xyz=True):
+        p = CellParams(0, 0, 0, 0, 0)
+        if out is None and want_xyz:
+            out = np.zeros((self.n, 3))
+        self._check(self.lib.b200vor_slab_lloyd(self.h, int(iters), ctypes.byref(p), _ptr(out), 0))
+        return out
+
+    def slab_lloyd_device(self, iters, xyz_out_ptr=None):
+        p = CellParams(0, 0, 0, 0, 0)
+        self._check(self.lib.b200vor_slab_lloyd(self.h, int(iters), ctypes.byref(p),
+                                                _ptr(int(xyz_out_ptr)) if xyz_out_ptr else None, 1))
+
+    def slab_stats(self):
+        s = SlabStats()
+        self._check(self.lib.b200vor_slab_get_stats(self.h, ctypes.byref(s)))
+        return {name: getattr(s, name) for name, _ in s._fields_}
 
     def exact_signs(self, planes):
         """planes: (n, 4, 4) float64 -- rows P0, P1, P2, P; returns the exact signs computed on the device"""

@@ -272,7 +272,8 @@ int cells_pipeline(Ctx* c, const b200vor_cell_params* params, bool collect_event
             }
         }
     }
-    for(int pass = pass0; pass < 8 && nq > 0; ++pass) {
+    // (the kNN-table fallback knows nothing of open faces: on a slab-local grid the flags stay)
+    for(int pass = pass0; pass < 8 && nq > 0 && !c->open; ++pass) {
         uint32_t rl = row_len(k);
         if((rc = c->knn.reserve(size_t(nq) * rl)) || (rc = c->knn_flag.reserve(nq))) {
             return rc;
@@ -394,13 +395,14 @@ int ensure_grid(Ctx* c) {
 }
 
 }  // namespace
+
+int ctx_build_grid_timed(Ctx* c) { return ensure_grid(c); }
+int ctx_cells(Ctx* c, const b200vor_cell_params* params, bool collect_events) {
+    return cells_pipeline(c, params, collect_events);
+}
 }  // namespace b200vor
 
 using namespace b200vor;
-
-struct b200vor_ctx {
-    Ctx c;
-};
 
 extern "C" {
 
@@ -448,6 +450,7 @@ void b200vor_destroy(b200vor_ctx* h) {
     Ctx& c = h->c;
     cudaSetDevice(c.device);
     cudaStreamSynchronize(c.stream);
+    slab_release(&c);
     c.xyz.release(); c.wgt.release(); c.cellid.release(); c.rank.release();
     c.sub.release(); c.vstart.release(); c.vcount.release(); c.wloc.release(); c.wloc_tmp.release();
     c.cell_start.release(); c.perm.release(); c.scan_tmp.release(); c.sorted.release();
@@ -472,6 +475,7 @@ int b200vor_set_domain_box(b200vor_ctx* h, const double* box) {
             return B200VOR_ERR_ARG;
         }
     }
+    slab_deactivate(&h->c);   // (a slab run captures the domain again at its next set_points)
     memcpy(h->c.box, box, 6 * sizeof(double));
     h->c.periodic = 0;
     h->c.cells_valid = h->c.faces_valid = false;
@@ -488,6 +492,7 @@ int b200vor_set_domain_periodic(b200vor_ctx* h, double period) {
         set_error("b200vor_set_domain_periodic: n too large for 32-bit periodic ids");
         return B200VOR_ERR_ARG;
     }
+    slab_deactivate(&h->c);
     h->c.periodic = 1;
     h->c.period = period;
     h->c.cells_valid = h->c.faces_valid = false;
@@ -542,6 +547,7 @@ int b200vor_set_points(b200vor_ctx* h, uint32_t n, const double* xyz, uint32_t s
     }
     Ctx* c = &h->c;
     B200_CUDA_CHECK(cudaSetDevice(c->device));
+    slab_deactivate(c);
     int rc;
     if((rc = c->xyz.reserve(3 * size_t(n)))) {
         return rc;
@@ -714,9 +720,9 @@ int b200vor_get_cells(b200vor_ctx* h, double* m, double* mg, uint8_t* status, in
     Ctx* c = &h->c;
     B200_CUDA_CHECK(cudaSetDevice(c->device));
     int rc;
-    if((m && (rc = copy_out(m, c->m.p, size_t(c->n) * sizeof(double), on_device, c->stream))) ||
-       (mg && (rc = copy_out(mg, c->mg.p, 3 * size_t(c->n) * sizeof(double), on_device, c->stream))) ||
-       (status && (rc = copy_out(status, c->status.p, size_t(c->n), on_device, c->stream)))) {
+    if((m && (rc = copy_out(m, c->m.p, size_t(out_rows(c)) * sizeof(double), on_device, c->stream))) ||
+       (mg && (rc = copy_out(mg, c->mg.p, 3 * size_t(out_rows(c)) * sizeof(double), on_device, c->stream))) ||
+       (status && (rc = copy_out(status, c->status.p, size_t(out_rows(c)), on_device, c->stream)))) {
         return rc;
     }
     B200_CUDA_CHECK(cudaStreamSynchronize(c->stream));
@@ -826,8 +832,8 @@ int b200vor_get_faces(b200vor_ctx* h, uint32_t* nfaces, uint32_t* face_nbr, doub
     }
     B200_CUDA_CHECK(cudaSetDevice(c->device));
     int rc;
-    size_t cnt = size_t(c->n) * fcap;
-    if((nfaces && (rc = copy_out(nfaces, c->nfaces.p, size_t(c->n) * sizeof(uint32_t), on_device, c->stream))) ||
+    size_t cnt = size_t(out_rows(c)) * fcap;
+    if((nfaces && (rc = copy_out(nfaces, c->nfaces.p, size_t(out_rows(c)) * sizeof(uint32_t), on_device, c->stream))) ||
        (face_nbr && (rc = copy_out(face_nbr, c->face_nbr.p, cnt * sizeof(uint32_t), on_device, c->stream))) ||
        (face_area && (rc = copy_out(face_area, c->face_area.p, cnt * sizeof(double), on_device, c->stream)))) {
         return rc;

@@ -76,6 +76,8 @@ struct Ctx {
     double period = 1.0;
     double box[6] = {0, 0, 0, 1, 1, 1};
     double ppc = 8.0;
+    int open = 0;              // slab-local context: open faces of the local grid (GridDesc::open)
+    struct Slab* slab = nullptr;   // multi-GPU slab state (slab.cu), or NULL
 
     uint32_t n = 0;
     uint32_t q0 = 0, q1 = 0xFFFFFFFFu;   // user-index range of the cells to compute
@@ -163,7 +165,19 @@ int reduce_events(Ctx* c);
 bool tpc_applicable(const Ctx* c);
 int run_cells_tpc(Ctx* c, uint32_t nq, const uint32_t* qlist, int want_faces, int collect_events, int big);
 int exact_sign_selftest(Ctx* c, uint32_t n, const double* planes_host, int* out_host);
+// capi.cu (used by slab.cu)
+int ctx_build_grid_timed(Ctx* c);
+int ctx_cells(Ctx* c, const b200vor_cell_params* params, bool collect_events);
+// slab.cu
+void slab_release(Ctx* c);
+uint32_t out_rows(const Ctx* c);   // rows the result getters return: n, or the own rows of a slab
+void slab_deactivate(Ctx* c);      // back to a plain single-GPU context (b200vor_set_points)
 // microbench.cu
 int microbench(Ctx* c, b200vor_peaks* out);
 
 }  // namespace b200vor
+
+// the opaque handle of the C ABI
+struct b200vor_ctx {
+    b200vor::Ctx c;
+};

@@ -388,6 +388,7 @@ int build_grid_impl(Ctx* c) {
     GridDesc& G = c->grid;
     G.periodic = c->periodic;
     G.period = c->period;
+    G.open = c->open;
     double lo[3], hi[3];
     if(c->periodic) {
         for(int a = 0; a < 3; ++a) {

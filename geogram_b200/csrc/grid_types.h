@@ -26,6 +26,10 @@ struct GridDesc {
     // vstart[] is the start table of the virtual cells (x fastest inside a bin)
     int two_level;
     uint32_t nvirt;
+    // slab-local grid (slab.cu): bit f of `open` = face f of the grid (x-,x+,y-,y+,z-,z+) is not a
+    // face of the domain: seeds this rank does not hold lie behind it, so the scanned block never
+    // covers more than the grid there and a cell that still needs more is left UNCERTIFIED
+    int open;
 };
 constexpr uint32_t kDenseBin = 32;   // a uniform (Poisson, 8 per bin) input never reaches it
 constexpr uint32_t kSubPpc = 8;      // sub-grid sized for <= kSubPpc seeds per virtual cell

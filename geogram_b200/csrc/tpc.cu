@@ -79,8 +79,8 @@ int exact_sign_selftest(Ctx* c, uint32_t n, const double* planes_host, int* out_
 // can the thread-per-cell kernel take the cells of this context?  (unweighted, single-level grid,
 // at least a 3x3x3 block of bins on a periodic domain, ids that fit 27 bits)
 bool tpc_applicable(const Ctx* c) {
-    if(c->has_w || c->grid.two_level || c->n >= (1u << 27)) {
-        return false;
+    if(c->has_w || c->grid.two_level || c->n >= (1u << 27) || c->open) {
+        return false;   // (a slab-local grid with open faces is walked by the team kernel only)
     }
     if(c->periodic) {
         const int gmin = std::min(c->grid.g[0], std::min(c->grid.g[1], c->grid.g[2]));

@@ -233,6 +233,41 @@ int b200vor_microbench(b200vor_ctx* ctx, b200vor_peaks* peaks);
  * planes (16 doubles: P0, P1, P2, P, host memory) the sign of P at the point P0 ^ P1 ^ P2
  * (-1, 0, +1; 2 = the three planes do not meet in one point) */
 int b200vor_selftest_exact_sign(b200vor_ctx* ctx, uint32_t n, const double* planes, int* signs);
+/* ---- multi-GPU: x-slabs with halos of ghost seeds, one process per GPU (the reference
+ *      is single-address-space, its hint is delaunay/periodic_delaunay_3d.cpp:3432-3436) ----
+ * Rank r owns the rows [first_global, first_global + n_own) of a global array of n_total seeds (hand
+ * every rank an x-slab: sort by x, split evenly).  The domain is the one set with
+ * b200vor_set_domain_box / _periodic before the first b200vor_slab_set_points.  A cell pass exchanges
+ * only the seeds within a halo of the neighbouring slabs (ncclSend / ncclRecv), bins the own + ghost
+ * seeds on a slab-local grid and computes the own cells; a cell whose security radius leaves the halo
+ * is re-queued with a doubled halo (all ranks).  Results: b200vor_get_cells / _get_faces return the
+ * n_own rows of this rank; neighbour ids are GLOBAL (index + n_total * instance on a periodic domain,
+ * delaunay/periodic.h:95-113).  world == 1 needs no communicator (ghosts = periodic images only). */
+#define B200VOR_UNIQUE_ID_BYTES 128
+typedef struct b200vor_slab_stats {
+    uint32_t n_own, n_ghost_x, n_ghost_yz, n_local;   /* seeds on the slab-local grid of the last pass   */
+    uint32_t retries;      /* halo doublings of the last pass                                            */
+    uint32_t n_flagged;    /* cells (all ranks) that still left the halo after the last pass             */
+    double halo;           /* halo width of the last pass                                                */
+    double slab_lo, slab_hi;
+    float ms_exchange, ms_pack, ms_grid, ms_clip;   /* device ms, summed over the passes of the last call */
+    uint64_t bytes_sent, bytes_received;            /* ghost traffic of this rank over the last call      */
+} b200vor_slab_stats;
+/* rank 0 creates the id (an ncclUniqueId), the caller hands the 128 bytes to every rank (MPI, torch, files) */
+int b200vor_comm_unique_id(void* id);
+/* collective: binds the context to rank `rank` of `world` (ncclCommInitRank; libnccl.so.2 is loaded on demand) */
+int b200vor_comm_init(b200vor_ctx* ctx, const void* id, int rank, int world);
+/* initial halo width in bins of the global seed density (default 3) */
+int b200vor_slab_set_halo_bins(b200vor_ctx* ctx, double bins);
+int b200vor_slab_set_points(b200vor_ctx* ctx, uint32_t n_own, uint64_t first_global, uint64_t n_total,
+                            const double* xyz, const double* w, int on_device);
+/* collective: one cell pass over the own seeds (params as b200vor_compute_cells; team kernel path) */
+int b200vor_slab_compute_cells(b200vor_ctx* ctx, const b200vor_cell_params* params);
+/* collective: `iters` Lloyd iterations (CVT.cpp:133-169); xyz_out_own: NULL or 3 n_own doubles */
+int b200vor_slab_lloyd(b200vor_ctx* ctx, uint32_t iters, const b200vor_cell_params* params,
+                       double* xyz_out_own, int on_device);
+int b200vor_slab_get_stats(b200vor_ctx* ctx, b200vor_slab_stats* stats);
+
 /* tuning knob: target points per grid cell (default 8.0); takes effect at the next set_points */
 int b200vor_set_points_per_cell(b200vor_ctx* ctx, double ppc);
 

@@ -44,6 +44,7 @@ extern "C" int tpc_host_cells_ex(uint32_t n, const double* xyz, int periodic, do
     G.periodic = periodic;
     G.period = period;
     G.two_level = 0;
+    G.open = 0;
     double lo[3], hi[3];
     for(int a = 0; a < 3; ++a) {
         if(periodic) {
