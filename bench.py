@@ -279,6 +279,8 @@ def main():
     ap.add_argument("--k0", type=int, default=0)
     ap.add_argument("--mode", type=int, default=0)
     ap.add_argument("--ppc", type=float, default=0.0)
+    ap.add_argument("--sharding", default="slab", choices=["slab", "replicated"],
+                    help="N>1: x-slabs with halo exchange inside the library (default) or every rank holds all seeds")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -329,8 +331,12 @@ def main():
     if args.ppc > 0:
         ctx.set_points_per_cell(args.ppc)
     peaks = ctx.microbench() if rank == 0 else None
-    from geogram_b200.sharding import ShardedLloyd
-    job = ShardedLloyd(ctx, n_total, dist if world > 1 else None, dev, stream)
+    from geogram_b200.sharding import ShardedLloyd, SlabLloyd
+    use_slab = world > 1 and args.sharding == "slab"
+    if use_slab:
+        job = SlabLloyd(ctx, n_total, dist, dev, stream)
+    else:
+        job = ShardedLloyd(ctx, n_total, dist if world > 1 else None, dev, stream)
     lo, hi = job.first, job.last
 
     def step():
@@ -370,7 +376,7 @@ def main():
     launches = ctx.stats()["gpu_launches"] - launches0
     last = ctx.stats()
     phase = dict(job.phase)
-    phase["ms_allgather"] = job.comm_ms()
+    phase["ms_exchange" if use_slab else "ms_allgather"] = job.comm_ms()
     if world > 1:
         t = torch.tensor([ms] + ms_iter, dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -523,12 +529,17 @@ def main():
                                "1..%d from the raw seeds (warm-up ran on a scratch copy)" % (n_total, args.steps)
                                if world == 1 else
                                "BASELINE configs[4]: weak scaling, %d uniform periodic seeds per GPU, Lloyd iterations "
-                               "1..%d from the raw seeds, x-quantile slab per rank, seeds all-gathered over NCCL"
-                               % (n_per, args.steps),
+                               "1..%d from the raw seeds, x-quantile slab per rank, %s"
+                               % (n_per, args.steps,
+                                  "halo of ghost seeds exchanged with ncclSend/Recv inside the library, slab-local grid"
+                                  if use_slab else "seeds all-gathered over NCCL, every rank bins all seeds"),
                    "seeds_per_gpu": n_per, "seeds_total": n_total,
                    "k_pass": last["k_pass"][: last["passes"]],
                    "cells_per_pass": last["n_pass"][: last["passes"]],
                    "grid": last["grid_dim"], "mode": args.mode,
+                   "sharding": (args.sharding if world > 1 else None),
+                   "slab": (job.last_stats if use_slab else None),
+                   "halo_retries": (job.retries if use_slab else None),
                    "l2": "inputs (>= 240 MB/step) exceed the 126 MB L2"},
         "phase_ms_per_step": per_step,
         "roofline": roofline, "cpu_baseline": cpu,

@@ -123,6 +123,7 @@ struct Slab {
     double H = 0.0;
     std::vector<double> lo, hi;            // slab bounds of every rank
     double wmax_global = 0.0;
+    double center = 0.0;                   // periodic domain: the own seeds are taken at their image next to it
     bool bounds_valid = false;             // lo / hi describe the current own seeds
     b200vor_slab_stats st = {};
     cudaEvent_t ev[4] = {};
@@ -134,19 +135,25 @@ namespace {
 // bucketed stable compaction: item i goes to every bucket b whose bit is set in mask(i); inside a
 // bucket the entries keep the order of the items.  count -> exclusive scan (bucket-major) -> scatter
 // ---------------------------------------------------------------------------------------------
+// image of the x-period that brings x next to `center` (0 on a box domain)
+__device__ inline int home_image(double x, double center, double period, int periodic) {
+    return periodic ? -int(rint((x - center) / period)) : 0;
+}
+
 struct XPred {
     // buckets q = 3 p + (s + 1): own seed i, image s of the x-period, wanted by peer p
     const double* own;
     uint32_t n;
     int world, rank, periodic;
-    double period, H;
+    double period, H, center;
     double lo[kMaxWorld], hi[kMaxWorld];
     __device__ uint32_t mask(uint32_t i) const {
         const double x = own[3 * size_t(i)];
+        const int s0 = home_image(x, center, period, periodic);   // the image this rank keeps as its own row
         uint32_t m = 0;
         for(int p = 0; p < world; ++p) {
             for(int s = -1; s <= 1; ++s) {
-                if((s != 0 && !periodic) || (s == 0 && p == rank)) {
+                if((s != 0 && !periodic) || (s == s0 && p == rank)) {
                     continue;
                 }
                 const double xs = x + double(s) * period;
@@ -328,15 +335,17 @@ __global__ void bucket_scatter_kernel(Pred P, Emit E, uint32_t nbuckets, uint32_
     }
 }
 
-// [min x, max x] of the seeds `xyz` (+ max weight, + number of own cells whose status meets `mask`):
-// one partial (4 doubles) per block
+// [min x, max x] of the seeds `xyz`, each taken at its image next to `center` (a slab of a periodic
+// domain is an arc: seeds that Lloyd wrapped around the period stay next to their slab), + max weight,
+// + number of own cells whose status meets `mask`: one partial (4 doubles) per block
 __global__ void bounds_kernel(const double* __restrict__ xyz, const double* __restrict__ w,
-                              const uint8_t* __restrict__ status, uint8_t mask, uint32_t n,
-                              double* __restrict__ part) {
+                              const uint8_t* __restrict__ status, uint8_t mask, uint32_t n, int periodic,
+                              double period, double center, double* __restrict__ part) {
     __shared__ double sm[4][8];
     double mn = 1e300, mx = -1e300, wm = -1e300, fl = 0.0;
     for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const double x = xyz[3 * size_t(i)];
+        double x = xyz[3 * size_t(i)];
+        x += double(home_image(x, center, period, periodic)) * period;
         mn = fmin(mn, x);
         mx = fmax(mx, x);
         if(w) {
@@ -373,6 +382,36 @@ __global__ void bounds_kernel(const double* __restrict__ xyz, const double* __re
     }
 }
 
+// circular mean of the own x: partial sums of (cos, sin)(2 pi x / period), fixed order
+__global__ void circular_mean_kernel(const double* __restrict__ xyz, uint32_t n, double period,
+                                     double* __restrict__ part) {
+    __shared__ double sm[2][8];
+    double c = 0.0, sn = 0.0;
+    for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        double sv, cv;
+        sincospi(2.0 * xyz[3 * size_t(i)] / period, &sv, &cv);
+        c += cv;
+        sn += sv;
+    }
+    for(int o = 16; o > 0; o >>= 1) {
+        c += __shfl_xor_sync(0xffffffffu, c, o);
+        sn += __shfl_xor_sync(0xffffffffu, sn, o);
+    }
+    if((threadIdx.x & 31) == 0) {
+        sm[0][threadIdx.x >> 5] = c;
+        sm[1][threadIdx.x >> 5] = sn;
+    }
+    __syncthreads();
+    if(threadIdx.x == 0) {
+        for(int k = 1; k < 8; ++k) {
+            c += sm[0][k];
+            sn += sm[1][k];
+        }
+        part[2 * blockIdx.x] = c;
+        part[2 * blockIdx.x + 1] = sn;
+    }
+}
+
 // partials -> out[0..3] = min, max, wmax, flagged (one thread: a few hundred values)
 __global__ void bounds_final_kernel(const double* __restrict__ part, int nb, double* __restrict__ out) {
     double mn = 1e300, mx = -1e300, wm = -1e300, fl = 0.0;
@@ -388,21 +427,25 @@ __global__ void bounds_final_kernel(const double* __restrict__ part, int nb, dou
     out[3] = fl;
 }
 
-// local arrays: rows [0, n_own) = the own seeds, rows [n_own, n_own + n_ghost) = received ghosts
+// local arrays: rows [0, n_own) = the own seeds (at their image next to the slab centre), rows
+// [n_own, n_own + n_ghost) = received ghosts
 __global__ void assemble_kernel(uint32_t n_own, uint32_t n_ghost, const double* __restrict__ own,
                                 const double* __restrict__ own_w, const double* __restrict__ ghosts,
-                                uint64_t first, double* __restrict__ xyz, double* __restrict__ w,
+                                uint64_t first, int periodic, double period, double center,
+                                double* __restrict__ xyz, double* __restrict__ w,
                                 uint32_t* __restrict__ lgid, uint8_t* __restrict__ ltc) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if(i < n_own) {
-        xyz[3 * size_t(i)] = own[3 * size_t(i)];
+        const double x = own[3 * size_t(i)];
+        const int s0 = home_image(x, center, period, periodic);
+        xyz[3 * size_t(i)] = x + double(s0) * period;
         xyz[3 * size_t(i) + 1] = own[3 * size_t(i) + 1];
         xyz[3 * size_t(i) + 2] = own[3 * size_t(i) + 2];
         if(w) {
             w[i] = own_w[i];
         }
         lgid[i] = uint32_t(first + i);
-        ltc[i] = uint8_t(1u | (1u << 2) | (1u << 4));
+        ltc[i] = uint8_t(uint32_t(s0 + 1) | (1u << 2) | (1u << 4));
     } else if(i < n_own + n_ghost) {
         const double* g = ghosts + size_t(i - n_own) * kGhostDoubles;
         xyz[3 * size_t(i)] = g[0];
@@ -435,8 +478,10 @@ __global__ void remap_faces_kernel(uint32_t n_own, uint32_t fcap, const uint32_t
         if(j < B200VOR_BOX_ID) {
             uint32_t inst = 0;
             if(periodic) {
+                // translation of the neighbour RELATIVE to the image the cell's own seed is kept at
                 const uint32_t t = ltc[j];
-                inst = translation_to_instance(int(t & 3u) - 1, int((t >> 2) & 3u) - 1, int((t >> 4) & 3u) - 1);
+                const int tx = clampi(int(t & 3u) - int(ltc[i] & 3u), -1, 1);
+                inst = translation_to_instance(tx, int((t >> 2) & 3u) - 1, int((t >> 4) & 3u) - 1);
             }
             ids[k] = lgid[j] + inst * n_total;
         }
@@ -452,6 +497,18 @@ __global__ void remap_faces_kernel(uint32_t n_own, uint32_t fcap, const uint32_t
         }
         ids[q] = id;
         ar[q] = a;
+    }
+}
+
+// m g of a cell is computed at the image its own seed is kept at: back to the caller's frame
+__global__ void mg_frame_kernel(uint32_t n_own, const uint8_t* __restrict__ ltc, const double* __restrict__ m,
+                                double period, double* __restrict__ mg) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i < n_own) {
+        const int s0 = int(ltc[i] & 3u) - 1;
+        if(s0 != 0) {
+            mg[3 * size_t(i)] -= double(s0) * period * m[i];
+        }
     }
 }
 
@@ -508,7 +565,7 @@ int exchange_bounds(Ctx* c, const double* xyz, const uint8_t* status, uint64_t* 
     }
     bounds_kernel<<<nb, 256, 0, c->stream>>>(xyz, S->has_w ? S->own_w.p : nullptr, status,
                                              uint8_t(B200VOR_CELL_UNCERTIFIED | B200VOR_CELL_BOXFACE), S->n_own,
-                                             S->red.p);
+                                             S->dom_periodic, S->dom_period, S->center, S->red.p);
     double* mine = S->gather_dev.p + 4 * size_t(S->world);
     bounds_final_kernel<<<1, 1, 0, c->stream>>>(S->red.p, nb, mine);
     c->stats.gpu_launches += 2;
@@ -561,6 +618,7 @@ int build_local(Ctx* c) {
     xp.periodic = S->dom_periodic;
     xp.period = S->dom_periodic ? S->dom_period : 0.0;
     xp.H = S->H;
+    xp.center = S->center;
     for(int p = 0; p < W; ++p) {
         xp.lo[p] = S->lo[p];
         xp.hi[p] = S->hi[p];
@@ -658,7 +716,8 @@ int build_local(Ctx* c) {
         return rc;
     }
     assemble_kernel<<<(nx + 255) / 256, 256, 0, st>>>(n_own, nrecv, S->own.p, S->has_w ? S->own_w.p : nullptr,
-                                                      S->recvbuf.p, S->first, c->xyz.p,
+                                                      S->recvbuf.p, S->first, S->dom_periodic, S->dom_period,
+                                                      S->center, c->xyz.p,
                                                       S->has_w ? c->wgt.p : nullptr, S->lgid.p, S->ltc.p);
     c->stats.gpu_launches++;
     if(S->dom_periodic) {
@@ -820,6 +879,11 @@ int slab_pass(Ctx* c, const b200vor_cell_params* params, bool lloyd) {
             return rc;
         }
         S->st.ms_clip += c->stats.ms_clip;
+        if(S->dom_periodic) {
+            mg_frame_kernel<<<(S->n_own + 255) / 256, 256, 0, c->stream>>>(S->n_own, S->ltc.p, c->m.p, S->dom_period,
+                                                                           c->mg.p);
+            c->stats.gpu_launches++;
+        }
         SLAB_TRACE(c, "cells done");
         if(lloyd) {
             lloyd_own_kernel<<<(S->n_own + 255) / 256, 256, 0, c->stream>>>(
@@ -1009,6 +1073,29 @@ int b200vor_slab_set_points(b200vor_ctx* h, uint32_t n_own, uint64_t first_globa
     S->first = first_global;
     S->n_total = n_total;
     S->H = initial_halo(S, c->ppc);
+    S->center = 0.0;
+    if(S->dom_periodic) {
+        // centre of the arc the own seeds occupy on the period: their circular mean (kept for the run)
+        const int nb = 296;
+        if((rc = S->red.reserve(4 * nb + 8))) {
+            return rc;
+        }
+        circular_mean_kernel<<<nb, 256, 0, c->stream>>>(S->own.p, n_own, S->dom_period, S->red.p);
+        c->stats.gpu_launches++;
+        double part[2 * nb];
+        B200_CUDA_CHECK(cudaMemcpyAsync(part, S->red.p, sizeof(part), cudaMemcpyDeviceToHost, c->stream));
+        B200_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        double cs = 0.0, sn = 0.0;
+        for(int b = 0; b < nb; ++b) {
+            cs += part[2 * b];
+            sn += part[2 * b + 1];
+        }
+        double a = atan2(sn, cs) / (2.0 * M_PI);   // in (-1/2, 1/2]
+        if(a < 0.0) {
+            a += 1.0;
+        }
+        S->center = a * S->dom_period;
+    }
     S->active = true;
     S->bounds_valid = false;
     c->cells_valid = c->faces_valid = false;

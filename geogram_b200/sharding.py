@@ -181,3 +181,76 @@ class ShardedLloyd(object):
         s = self.ctx.stats()
         for k in keys:
             self.phase[k] += s[k]
+
+
+class SlabLloyd(object):
+    """CVT Lloyd relaxation over the GPUs of one node with x-SLABS AND HALOS (one process per GPU):
+    the driver of b200vor_slab_* (csrc/slab.cu).  Rank r keeps only its own rows [first, last) of the
+    x-sorted seed array on the device; every iteration it exchanges the seeds within a halo of the
+    neighbouring slabs (ncclSend / ncclRecv inside the library), bins own + ghost seeds on a
+    slab-local grid and updates its own seeds.  No rank ever holds, bins or receives all seeds.
+    Same interface as ShardedLloyd (the replicated variant above).
+
+    `dist` (torch.distributed, initialised) is used ONCE, to hand the NCCL id of the library's own
+    communicator to every rank."""
+
+    def __init__(self, ctx, n_total, dist=None, device=None, stream=None, halo_bins=None):
+        import torch
+        self.torch = torch
+        self.ctx = ctx
+        self.dist = dist
+        self.world = dist.get_world_size() if dist is not None else 1
+        self.rank = dist.get_rank() if dist is not None else 0
+        self.n_total = int(n_total)
+        self.first, self.last = shard_range(self.n_total, self.rank, self.world)
+        self.device = device
+        self.stream = stream if stream is not None else torch.cuda.current_stream(device)
+        ctx.set_stream(self.stream.cuda_stream)
+        if self.world > 1:
+            from .capi import Context
+            uid = [Context.comm_unique_id() if self.rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            ctx.comm_init(uid[0], self.rank, self.world)
+        if halo_bins:
+            ctx.slab_set_halo_bins(halo_bins)
+        self.mine = torch.empty((self.last - self.first, 3), dtype=torch.float64, device=device)
+        self.order = None
+        self.phase = {"ms_grid": 0.0, "ms_knn": 0.0, "ms_clip": 0.0}
+        self._comm_ms = 0.0
+        self.retries = 0
+        self.last_stats = None
+
+    def set_seeds_device(self, full, slabs=True):
+        """full: (n_total,3) float64 device tensor of ALL seeds, identical on every rank (set-up
+        only): sorted by x once, this rank keeps its rows."""
+        with self.torch.cuda.stream(self.stream):
+            self.order = slab_order(full) if slabs else None
+            rows = full[self.order[self.first:self.last]] if slabs else full[self.first:self.last]
+            self.mine.copy_(rows)
+        self.stream.synchronize()
+        self.ctx.slab_set_points_device(self.last - self.first, self.first, self.n_total, self.mine.data_ptr())
+
+    def set_shard_host(self, host_rows):
+        with self.torch.cuda.stream(self.stream):
+            self.mine.copy_(host_rows, non_blocking=True)
+        self.ctx.slab_set_points_device(self.last - self.first, self.first, self.n_total, self.mine.data_ptr())
+
+    def step(self, k0=0, mode=0):
+        self.ctx.slab_lloyd_device(1, None)
+        s = self.ctx.slab_stats()
+        self.last_stats = s
+        self.phase["ms_grid"] += s["ms_grid"]
+        self.phase["ms_clip"] += s["ms_clip"]
+        self._comm_ms += s["ms_exchange"] + s["ms_pack"]
+        self.retries += s["retries"]
+
+    def get_shard_host(self, host_rows):
+        self.ctx.slab_lloyd_device(0, self.mine.data_ptr())
+        with self.torch.cuda.stream(self.stream):
+            host_rows.copy_(self.mine, non_blocking=True)
+        self.stream.synchronize()
+        return host_rows
+
+    def comm_ms(self):
+        ms, self._comm_ms = self._comm_ms, 0.0
+        return ms

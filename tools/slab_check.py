@@ -61,6 +61,7 @@ def main():
             assert np.abs(fa[live] - fa0[sl][live]).max() < 1e-12
             err = np.abs(m - m0[sl]).max() / m0.max()
             assert err < 1e-12, err
+            assert np.abs(mg - mg0[sl]).max() <= 1e-12 * m0.max()
             worst = max(worst, err)
             if world > 1:
                 assert s["n_ghost_x"] > 0 and s["bytes_sent"] > 0, s
