@@ -254,3 +254,98 @@ class SlabLloyd(object):
     def comm_ms(self):
         ms, self._comm_ms = self._comm_ms, 0.0
         return ms
+
+
+# ---- host statement of the halo selection of csrc/slab.cu (XPred / YZPred), numpy: what a rank must
+#      hold to compute its own cells.  Used by the CPU tests (gloo) and as the specification of the
+#      device kernels; the product path never calls it. ----
+def home_image(x, center, period):
+    """image of the x-period that brings x next to `center` (slab.cu: home_image)"""
+    import numpy as np
+    return -np.rint((x - center) / period).astype(np.int64)
+
+
+def circular_center(x, period):
+    import numpy as np
+    a = 2.0 * np.pi * x / period
+    c = np.arctan2(np.sin(a).sum(), np.cos(a).sum()) / (2.0 * np.pi)
+    return (c + 1.0 if c < 0.0 else c) * period
+
+
+def slab_bounds(x_own, period=None):
+    """(lo, hi, center) of a rank's own seeds; periodic: an arc around the circular mean"""
+    if period is None:
+        return float(x_own.min()), float(x_own.max()), 0.0
+    c = circular_center(x_own, period)
+    xu = x_own + home_image(x_own, c, period) * period
+    return float(xu.min()), float(xu.max()), float(c)
+
+
+def halo_send_list(xyz_own, first, rank, bounds, H, period=None):
+    """For every peer p: (rows of (x', y, z), global ids, x-images) of the own seeds (and their
+    x-images) within [lo_p - H, hi_p + H] -- own-index order inside each (peer, image) bucket."""
+    import numpy as np
+    x = xyz_own[:, 0]
+    s0 = home_image(x, bounds[rank][2], period) if period is not None else np.zeros(len(x), np.int64)
+    out = []
+    for p, (lo, hi, _) in enumerate(bounds):
+        rows, gids, imgs = [], [], []
+        for s in (-1, 0, 1):
+            if s != 0 and period is None:
+                continue
+            xs = x + (s * period if period is not None else 0.0)
+            sel = (xs >= lo - H) & (xs <= hi + H)
+            if p == rank:
+                sel &= s0 != s
+            idx = np.nonzero(sel)[0]
+            r = xyz_own[idx].copy()
+            r[:, 0] = xs[idx]
+            rows.append(r)
+            gids.append(first + idx)
+            imgs.append(np.full(len(idx), s, np.int64))
+        out.append((np.concatenate(rows), np.concatenate(gids), np.concatenate(imgs)))
+    return out
+
+
+def halo_local_set(xyz_own, first, rank, bounds, received, H, period=None):
+    """Local seed array of a rank: own rows (at their home image), received ghosts in peer order,
+    then (periodic) the y / z images within H of a face.  Returns (xyz, global id, (tx, ty, tz))."""
+    import numpy as np
+    own = xyz_own.copy()
+    tx0 = np.zeros(len(own), np.int64)
+    if period is not None:
+        tx0 = home_image(own[:, 0], bounds[rank][2], period)
+        own[:, 0] += tx0 * period
+    xyz = np.concatenate([own] + [r[0] for r in received])
+    gid = np.concatenate([first + np.arange(len(own))] + [r[1] for r in received])
+    tx = np.concatenate([tx0] + [r[2] for r in received])
+    t = np.stack([tx, np.zeros_like(tx), np.zeros_like(tx)], axis=1)
+    if period is None:
+        return xyz, gid, t
+    add_xyz, add_gid, add_t = [], [], []
+    for tz in (-1, 0, 1):
+        for ty in (-1, 0, 1):
+            if ty == 0 and tz == 0:
+                continue
+            y = xyz[:, 1] + ty * period
+            z = xyz[:, 2] + tz * period
+            sel = (y >= -H) & (y <= period + H) & (z >= -H) & (z <= period + H)
+            if ty == -1:
+                sel &= xyz[:, 1] >= period - H
+            if ty == 1:
+                sel &= xyz[:, 1] <= H
+            if tz == -1:
+                sel &= xyz[:, 2] >= period - H
+            if tz == 1:
+                sel &= xyz[:, 2] <= H
+            idx = np.nonzero(sel)[0]
+            r = xyz[idx].copy()
+            r[:, 1] = y[idx]
+            r[:, 2] = z[idx]
+            add_xyz.append(r)
+            add_gid.append(gid[idx])
+            tt = t[idx].copy()
+            tt[:, 1] = ty
+            tt[:, 2] = tz
+            add_t.append(tt)
+    return (np.concatenate([xyz] + add_xyz), np.concatenate([gid] + add_gid), np.concatenate([t] + add_t))

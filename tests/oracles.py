@@ -213,6 +213,12 @@ def face_mismatches(A, B):
     return int((bad | diff).sum())
 
 
+def translation_to_instance(tx, ty, tz):
+    """delaunay/periodic.h:104-113 + periodic.cpp:80-84 (reorder_instances): 13 -> 0, 0..12 -> 1..13"""
+    i = (int(tz) + 1) + 3 * (int(ty) + 1) + 9 * (int(tx) + 1)
+    return 0 if i == 13 else (i + 1 if i < 13 else i)
+
+
 def uniform_seeds(n, seed=12345):
     return np.random.default_rng(seed).random((n, 3))
 

@@ -170,3 +170,79 @@ def test_sharded_lloyd_gloo(world, n_total):
     # after the last step (a caller that uploads fresh seeds every step pays for one build, not two)
     assert calls == ["set_points", "lloyd"] + ["set_points", "lloyd"] * 2
     assert phase["ms_clip"] == 6.0 and phase["ms_grid"] == 3.0
+
+
+# ---- slab + halo (csrc/slab.cu): the host statement of the halo selection, exchanged over gloo, must
+#      give every rank exactly the seeds its own cells need: the cells the CPU oracle computes from
+#      the rank's LOCAL set (a plain box problem) are the cells of the periodic run on all seeds ----
+def _slab_worker(rank, world, port, n_total, periodic, q):
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracles
+    from geogram_b200.sharding import halo_local_set, halo_send_list, slab_bounds
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    xyz = np.random.default_rng(3).random((n_total, 3))
+    xyz = xyz[np.argsort(xyz[:, 0], kind="stable")]
+    # a few seeds wrapped around the period by a Lloyd step (rank 0 owns seeds next to x = 1)
+    if periodic:
+        xyz[:3, 0] = 1.0 - 1e-3 * (1 + np.arange(3))
+    first, last = shard_range(n_total, rank, world)
+    own = xyz[first:last]
+    period = 1.0 if periodic else None
+    H = 3.0 * (8.0 / n_total) ** (1.0 / 3.0)
+    bounds = [None] * world
+    dist.all_gather_object(bounds, slab_bounds(own[:, 0], period))
+    send = halo_send_list(own, first, rank, bounds, H, period)
+    inbox = [None] * world
+    for p in range(world):                 # peer p collects what every rank has for it
+        got = [None] * world
+        dist.all_gather_object(got, send[p])
+        if p == rank:
+            inbox = got
+    lx, lgid, lt = halo_local_set(own, first, rank, bounds, inbox, H, period)
+    lo, hi, _ = bounds[rank]
+    port_ = oracles.Port()
+    if periodic:
+        box = [lo - H, -H, -H, hi + H, 1.0 + H, 1.0 + H]
+    else:
+        box = [max(lo - H, 0.0), 0.0, 0.0, min(hi + H, 1.0), 1.0, 1.0]
+    L = port_.cells(lx, box=box)
+    G = port_.cells(xyz, periodic=periodic)
+    n_own = last - first
+    err = float(np.abs(L.m[:n_own] - G.m[first:last]).max() / G.m.max())
+    # same neighbours: local face ids -> global id + instance
+    bad = 0
+    for i in range(0, n_own, 7):
+        ids = L.face_nbr[i, : L.nfaces[i]]
+        loc = ids[ids < oracles.BOX_ID]
+        if periodic and len(loc) != len(ids):
+            bad += 1                      # a periodic cell never touches the local box
+        rel = lt[loc] - lt[i]
+        inst = np.array([oracles.translation_to_instance(*r) for r in rel], np.int64)
+        mine = np.sort(lgid[loc] + inst * n_total)
+        ref = G.face_nbr[first + i, : G.nfaces[first + i]]
+        ref = np.sort(ref[ref < oracles.BOX_ID].astype(np.int64))
+        bad += 0 if (len(mine) == len(ref) and (mine == ref).all()) else 1
+    t = torch.tensor([err, float(bad), float(len(lx))], dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        q.put((float(t[0]), float(t[1]), float(t[2])))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,periodic", [(2, True), (3, True), (2, False)])
+def test_slab_halo_plan_gloo(world, periodic):
+    n_total = 6000
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_slab_worker, args=(r, world, port, n_total, periodic, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    err, bad, nlocal = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert err < 1e-12 and bad == 0
