@@ -137,6 +137,9 @@ struct KnnJob {
     int user_ids;            // 1: ids and row order in user space; 0: grid order (+n*instance)
 };
 int run_knn(Ctx* c, const KnnJob& job);
+// knn_team.cu
+bool knn_team_applicable(const Ctx* c, const KnnJob& job);
+int run_knn_team(Ctx* c, const KnnJob& job, uint32_t* nfail);
 // cell.cu
 struct CellJob {
     uint32_t nq;

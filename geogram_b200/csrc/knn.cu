@@ -425,6 +425,15 @@ int run_knn(Ctx* c, const KnnJob& job) {
     if(job.nq == 0) {
         return B200VOR_OK;
     }
+    if(knn_team_applicable(c, job)) {
+        // team-per-query kernel (knn_team.cu); the heap kernel below takes the job again only if a
+        // query met more than a pool of seeds at one distance
+        uint32_t nfail = 0;
+        int rc0 = run_knn_team(c, job, &nfail);
+        if(rc0 || nfail == 0) {
+            return rc0;
+        }
+    }
     KnnParams P;
     P.G = c->grid;
     P.sorted = c->sorted.p;
