@@ -203,6 +203,8 @@ int cells_pipeline(Ctx* c, const b200vor_cell_params* params, bool collect_event
     c->stats.tpc_cells = 0;
     const uint32_t nq0 = nq;
     const uint32_t* const qlist0 = qlist;
+    // two-level grid on a box domain: far-reaching cells are swept by the large-cell instance (fused_kernel.inc)
+    const bool far_sweep = c->grid.two_level && !c->grid.periodic && p.mode != 1 && p.mode != 2;
     c->stats.exact_cells = 0;
     if((p.mode == 4 || (p.mode == 0 && kTpcFirstByDefault)) && p.want_faces <= 1 && !p.want_energy &&
        tpc_applicable(c)) {
@@ -232,6 +234,7 @@ int cells_pipeline(Ctx* c, const b200vor_cell_params* params, bool collect_event
     if(p.mode != 2 && nq > 0) {
         // team-kernel grid walk: one launch, no neighbour table (fused.cu)
         T.mark(2);
+        c->fused_bail_far = p.mode != 1;   // the large-cell instance follows
         if((rc = run_cells_fused(c, nq, qlist, int(p.want_faces), collect_events ? 1 : 0, 0.f,
                                  int(p.want_energy), 0))) {
             return rc;
@@ -260,6 +263,7 @@ int cells_pipeline(Ctx* c, const b200vor_cell_params* params, bool collect_event
                 nq = nfail;
                 if(big && nq > 0) {
                     T.mark(2);
+                    c->fused_no_sweep = false;
                     if((rc = run_cells_fused(c, nq, qlist, int(p.want_faces), collect_events ? 1 : 0, 0.f,
                                              int(p.want_energy), 1))) {
                         return rc;
@@ -270,10 +274,40 @@ int cells_pipeline(Ctx* c, const b200vor_cell_params* params, bool collect_event
                     c->stats.passes = ++pass0;
                 }
             }
+            if(nq > 0 && far_sweep) {
+                // two-level grid: the few far-reaching cells whose sweep ran out of capacity (clipping out
+                // of distance order piles up transient faces) walk their shells to the end instead
+                T.mark(2);
+                c->fused_no_sweep = true;
+                rc = run_cells_fused(c, nq, qlist, int(p.want_faces), collect_events ? 1 : 0, 0.f, int(p.want_energy), 1);
+                c->fused_no_sweep = false;
+                if(rc) {
+                    return rc;
+                }
+                T.mark(0);
+                if(pass0 < 8) {
+                    c->stats.n_pass[pass0] = nq;
+                    c->stats.k_pass[pass0] = 0;
+                    c->stats.passes = ++pass0;
+                }
+                if((rc = c->qlist.reserve(nq)) || (rc = c->qlist2.reserve(nq))) {
+                    return rc;
+                }
+                uint32_t* out = (qlist == c->qlist.p) ? c->qlist2.p : c->qlist.p;
+                uint32_t nfail = 0;
+                if((rc = compact_failed(c, qlist, nq, out, nullptr, &nfail,
+                                        B200VOR_CELL_UNCERTIFIED | B200VOR_CELL_OVERFLOW))) {
+                    return rc;
+                }
+                qlist = out;
+                nq = nfail;
+            }
         }
     }
     // (the kNN-table fallback knows nothing of open faces: on a slab-local grid the flags stay)
-    for(int pass = pass0; pass < 8 && nq > 0 && !c->open; ++pass) {
+    // (nor can a table of <= kmax neighbours certify the far-reaching cells of clustered seeds that
+    //  the large-cell instance gave up on: their flags stay too)
+    for(int pass = pass0; pass < 8 && nq > 0 && !c->open && !far_sweep; ++pass) {
         uint32_t rl = row_len(k);
         if((rc = c->knn.reserve(size_t(nq) * rl)) || (rc = c->knn_flag.reserve(nq))) {
             return rc;
@@ -452,7 +486,7 @@ void b200vor_destroy(b200vor_ctx* h) {
     cudaStreamSynchronize(c.stream);
     slab_release(&c);
     c.xyz.release(); c.wgt.release(); c.cellid.release(); c.rank.release();
-    c.sub.release(); c.vstart.release(); c.vcount.release(); c.wloc.release(); c.wloc_tmp.release();
+    c.sub.release(); c.vstart.release(); c.vcount.release(); c.sbcount.release(); c.wloc.release(); c.wloc_tmp.release();
     c.cell_start.release(); c.perm.release(); c.scan_tmp.release(); c.sorted.release();
     c.knn.release(); c.knn_flag.release(); c.qlist.release(); c.qlist2.release(); c.qlist3.release(); c.qrows.release();
     c.counter.release(); c.m.release(); c.mg.release(); c.status.release();

@@ -76,6 +76,8 @@ struct Ctx {
     double period = 1.0;
     double box[6] = {0, 0, 0, 1, 1, 1};
     double ppc = 8.0;
+    bool fused_no_sweep = false;   // (pipeline -> fused.cu) large-cell instance without the sweep
+    bool fused_bail_far = false;   // (pipeline -> fused.cu) far-reaching cells go straight to the large-cell instance
     int open = 0;              // slab-local context: open faces of the local grid (GridDesc::open)
     struct Slab* slab = nullptr;   // multi-GPU slab state (slab.cu), or NULL
 
@@ -90,6 +92,7 @@ struct Ctx {
     GridDesc grid;
     DevBuf<uint32_t> cellid, rank, cell_start, perm, scan_tmp;
     DevBuf<uint32_t> sub, vstart, vcount;   // two-level grid only
+    DevBuf<uint32_t> sbcount;               // two-level grid only: seeds per 8 x 8 x 8 block of bins
     DevBuf<double> wloc, wloc_tmp;          // Laguerre only: dilated per-bin weight maxima (near | far)
     DevBuf<Seed> sorted;
 

@@ -298,6 +298,23 @@ __global__ void sort_bins_kernel(uint32_t ncell, const uint32_t* __restrict__ ce
     }
 }
 
+// seeds per super-bin (8 x 8 x 8 bins): the coarse occupancy level of the two-level walk
+__global__ void superbin_count_kernel(GridDesc G, const uint32_t* __restrict__ cell_start,
+                                      uint32_t* __restrict__ sbcount) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if(b >= G.ncell) {
+        return;
+    }
+    const uint32_t cnt = cell_start[b + 1] - cell_start[b];
+    if(cnt == 0) {
+        return;
+    }
+    const uint32_t gx = uint32_t(G.g[0]), gy = uint32_t(G.g[1]);
+    const uint32_t ix = b % gx, iy = (b / gx) % gy, iz = b / (gx * gy);
+    const uint32_t sx = (gx + (1u << kSuperLog) - 1) >> kSuperLog, sy = (gy + (1u << kSuperLog) - 1) >> kSuperLog;
+    atomicAdd(&sbcount[(ix >> kSuperLog) + sx * ((iy >> kSuperLog) + sy * (iz >> kSuperLog))], cnt);
+}
+
 // ---- local weight bound (Laguerre cells): wloc[b] = max weight of the seeds in the bins within
 //      Chebyshev distance kWlocRing of bin b; lets the security radius use a LOCAL weight spread
 //      (fused_kernel.inc, sr_bound) when the weights vary smoothly over the domain ----
@@ -540,6 +557,16 @@ int build_grid_impl(Ctx* c) {
         G.nvirt, c->vstart.p, c->sorted.p, c->perm.p);
     level1_start_kernel<<<(G.ncell + 1 + kThreads - 1) / kThreads, kThreads, 0, st>>>(
         G.ncell, n, c->sub.p, c->vstart.p, c->cell_start.p);
+    {
+        const size_t nsb = size_t((G.g[0] + (1 << kSuperLog) - 1) >> kSuperLog) * size_t((G.g[1] + (1 << kSuperLog) - 1) >> kSuperLog) *
+                           size_t((G.g[2] + (1 << kSuperLog) - 1) >> kSuperLog);
+        if((rc = c->sbcount.reserve(nsb))) {
+            return rc;
+        }
+        B200_CUDA_CHECK(cudaMemsetAsync(c->sbcount.p, 0, nsb * sizeof(uint32_t), st));
+        superbin_count_kernel<<<(G.ncell + kThreads - 1) / kThreads, kThreads, 0, st>>>(G, c->cell_start.p, c->sbcount.p);
+        c->stats.gpu_launches++;
+    }
     c->stats.gpu_launches += 7;
     B200_CUDA_CHECK(cudaGetLastError());
     return B200VOR_OK;

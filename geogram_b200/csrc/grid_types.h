@@ -35,6 +35,7 @@ constexpr uint32_t kDenseBin = 32;   // a uniform (Poisson, 8 per bin) input nev
 constexpr uint32_t kSubPpc = 8;      // sub-grid sized for <= kSubPpc seeds per virtual cell
 constexpr int kMaxSubLog = 5;        // s <= 32
 constexpr int kSmallPeriodicGrid = 12; // periodic grids with fewer bins per axis take the two-level walk
+constexpr int kSuperLog = 3;           // two-level grid: occupancy of 8 x 8 x 8 blocks of bins (far-reaching cells skip empty space)
 constexpr int kWlocRingNear = 3;     // bins of dilation of the two local weight bounds (Laguerre)
 constexpr int kWlocRingFar = 8;
 
