@@ -56,6 +56,9 @@ namespace b200vor {
 #ifndef B200VOR_FUSED_WPB
 #define B200VOR_FUSED_WPB 8    // warps per block (8 x 2 cells share their neighbourhood in L1)
 #endif
+#ifndef B200VOR_FUSED_WPB_TWO
+#define B200VOR_FUSED_WPB_TWO 8   // warps per block on a two-level grid (2 and 8 measured: 915 vs 843 ms at 10 M clustered seeds)
+#endif
 #define B200VOR_FUSED_VARIANT fused_std
 #define B200VOR_FUSED_NT 48
 #define B200VOR_FUSED_PC 40
@@ -67,6 +70,7 @@ namespace b200vor {
 #undef B200VOR_FUSED_FC
 #undef B200VOR_FUSED_G
 #undef B200VOR_FUSED_WPB
+#undef B200VOR_FUSED_WPB_TWO
 #undef B200VOR_FUSED_MINBLOCKS
 
 // ---- large cells (what the standard instance flags OVERFLOW / UNCERTIFIED: transiently large
@@ -74,6 +78,7 @@ namespace b200vor {
 #define B200VOR_FUSED_VARIANT fused_big
 #define B200VOR_FUSED_G 32
 #define B200VOR_FUSED_WPB 4
+#define B200VOR_FUSED_WPB_TWO 4
 #define B200VOR_FUSED_MINBLOCKS 2
 #define B200VOR_FUSED_NT 128
 #define B200VOR_FUSED_PC 64
