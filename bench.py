@@ -249,6 +249,67 @@ def extra_configs(torch, dev, ctx, xyz_relaxed, n, args):
     return res
 
 
+def run_clustered(args, torch, dist, dev, rank, world, json_fd):
+    """BASELINE configs[3]: one cell pass over n Gaussian-mixture seeds in the unit box, the cells
+    sharded over the ranks by x-slab (b200vor_set_query_range); device time = max over ranks."""
+    from geogram_b200 import Context
+    from geogram_b200.sharding import shard_range, slab_order
+    n = args.seeds or 10000000
+    xyz = clustered_seeds_device(torch, n, dev)          # same generator seed on every rank: same seeds
+    xyz = xyz[slab_order(xyz)].contiguous()
+    first, last = shard_range(n, rank, world)
+    ctx = Context(dev.index)
+    ctx.set_domain_box([0, 0, 0, 1, 1, 1])
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    times = []
+    for it in range(args.warmup + args.steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        ctx.set_points_device(n, xyz.data_ptr())
+        if world > 1:
+            ctx.set_query_range(first, last)
+        ctx.compute_cells()
+        b.record()
+        torch.cuda.synchronize()
+        if it >= args.warmup:
+            times.append(a.elapsed_time(b))
+    s = ctx.stats()
+    m = torch.empty((n,), dtype=torch.float64, device=dev)
+    st = torch.empty((n,), dtype=torch.uint8, device=dev)
+    ctx.get_cells_device(m.data_ptr(), None, st.data_ptr())
+    m, st = m[first:last], st[first:last]
+    names = {1: "uncertified", 2: "uncertain", 4: "empty", 8: "boxface", 16: "overflow", 32: "duplicate", 64: "degenerate"}
+    counts = torch.tensor([float((st == 0).sum().item())] + [float(((st & bit) != 0).sum().item()) for bit in names]
+                          + [float(m.sum().item())], dtype=torch.float64, device=dev)
+    t = torch.tensor([sum(times) / len(times), s["ms_grid"], s["ms_clip"] + s["ms_knn"]], dtype=torch.float64, device=dev)
+    tmin = t.clone()
+    if world > 1:
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        c = counts.tolist()
+        line = {"metric": METRIC, "value": n / (float(t[0]) * 1e-3), "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(t[0]), "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "BASELINE configs[3]: %d Gaussian-mixture seeds (32 clusters, sigma 0.005..0.05), unit box, "
+                                       "one pass = grid build + cells (volume, centroid); cells sharded by x-slab over %d GPU(s), "
+                                       "every rank bins all seeds" % (n, world),
+                           "seeds_total": n, "grid": s["grid_dim"], "cells_per_pass_rank0": s["n_pass"][: s["passes"]]},
+                "phase_ms_per_step": {"ms_grid_max": float(t[1]), "ms_cells_max": float(t[2]), "ms_cells_min": float(tmin[2])},
+                "status": dict([("ok", int(c[0]))] + [(nm, int(c[1 + k])) for k, nm in enumerate(names.values())]),
+                "sum_m_minus_1": c[-1] - 1.0,
+                "cells_per_s_per_gpu": n / (float(t[0]) * 1e-3) / world,
+                "gpu_launches": int(s["gpu_launches"])}
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def load_inst_counts(n_cells):
     """Per-iteration instruction counts of the cell kernels from the committed ncu capture
     (profiles/r02_inst_by_iter.json, made by tools/ncu_inst_by_iter.sh from THIS bench command:
@@ -279,6 +340,10 @@ def main():
     ap.add_argument("--k0", type=int, default=0)
     ap.add_argument("--mode", type=int, default=0)
     ap.add_argument("--ppc", type=float, default=0.0)
+    ap.add_argument("--workload", default="lloyd", choices=["lloyd", "clustered"],
+                    help="lloyd: the headline (BASELINE configs[1] / [4]); clustered: BASELINE configs[3], one cell pass over "
+                         "--seeds Gaussian-mixture seeds IN TOTAL, the cells sharded over the GPUs by x-slab (every rank "
+                         "holds all seeds: far-reaching fringe cells need them)")
     ap.add_argument("--sharding", default="slab", choices=["slab", "replicated"],
                     help="N>1: x-slabs with halo exchange inside the library (default) or every rank holds all seeds")
     args = ap.parse_args()
@@ -309,6 +374,9 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
+    if args.workload == "clustered":
+        run_clustered(args, torch, dist, dev, rank, world, json_fd)
+        return
     n_per = args.seeds or (10000000 if world == 1 else 12500000)
     n_total = n_per * world
 

@@ -263,7 +263,7 @@ int cells_pipeline(Ctx* c, const b200vor_cell_params* params, bool collect_event
                 nq = nfail;
                 if(big && nq > 0) {
                     T.mark(2);
-                    c->fused_no_sweep = false;
+                    c->fused_sweep_mode = 0;
                     if((rc = run_cells_fused(c, nq, qlist, int(p.want_faces), collect_events ? 1 : 0, 0.f,
                                              int(p.want_energy), 1))) {
                         return rc;
@@ -274,13 +274,14 @@ int cells_pipeline(Ctx* c, const b200vor_cell_params* params, bool collect_event
                     c->stats.passes = ++pass0;
                 }
             }
-            if(nq > 0 && far_sweep) {
-                // two-level grid: the few far-reaching cells whose sweep ran out of capacity (clipping out
-                // of distance order piles up transient faces) walk their shells to the end instead
+            // two-level grid: the few far-reaching cells whose sweep ran out of capacity (clipping out of
+            // distance order piles up transient faces) are swept again in much finer distance bands, and
+            // what even that leaves walks its shells to the end
+            for(int sm = 1; sm <= 2 && nq > 0 && far_sweep; ++sm) {
                 T.mark(2);
-                c->fused_no_sweep = true;
+                c->fused_sweep_mode = sm;
                 rc = run_cells_fused(c, nq, qlist, int(p.want_faces), collect_events ? 1 : 0, 0.f, int(p.want_energy), 1);
-                c->fused_no_sweep = false;
+                c->fused_sweep_mode = 0;
                 if(rc) {
                     return rc;
                 }

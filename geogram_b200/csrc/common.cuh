@@ -76,7 +76,7 @@ struct Ctx {
     double period = 1.0;
     double box[6] = {0, 0, 0, 1, 1, 1};
     double ppc = 8.0;
-    bool fused_no_sweep = false;   // (pipeline -> fused.cu) large-cell instance without the sweep
+    int fused_sweep_mode = 0;      // (pipeline -> fused.cu) large-cell instance: 0 sweep in bands x4, 1 bands x1.25, 2 no sweep
     bool fused_bail_far = false;   // (pipeline -> fused.cu) far-reaching cells go straight to the large-cell instance
     int open = 0;              // slab-local context: open faces of the local grid (GridDesc::open)
     struct Slab* slab = nullptr;   // multi-GPU slab state (slab.cu), or NULL
