@@ -608,6 +608,7 @@ def main():
                    "sharding": (args.sharding if world > 1 else None),
                    "slab": (job.last_stats if use_slab else None),
                    "halo_retries": (job.retries if use_slab else None),
+                   "slab_steps_rank0": (job.steps[-(args.steps + e2e_steps):][: args.steps] if use_slab else None),
                    "l2": "inputs (>= 240 MB/step) exceed the 126 MB L2"},
         "phase_ms_per_step": per_step,
         "roofline": roofline, "cpu_baseline": cpu,

@@ -53,7 +53,7 @@ template <class T> struct DevBuf {
             p = nullptr;
             cap = 0;
         }
-        size_t want = n + n / 16 + 64;
+        size_t want = n + n / 8 + 64;   // (slack: sizes that drift upwards from call to call do not re-allocate each time)
         B200_CUDA_CHECK(cudaMalloc(&p, want * sizeof(T)));
         cap = want;
         return B200VOR_OK;

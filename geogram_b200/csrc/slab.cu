@@ -711,8 +711,11 @@ int build_local(Ctx* c) {
     // upper bound of the y / z images, refined below: reserve generously, then exactly
     uint32_t nyz = 0;
     const uint32_t nblk2 = (nx + kPackBlock - 1) / kPackBlock;
-    if((rc = c->xyz.reserve(3 * size_t(nx))) || (rc = S->lgid.reserve(nx)) || (rc = S->ltc.reserve(nx)) ||
-       (S->has_w && (rc = c->wgt.reserve(nx)))) {
+    // room for the y / z images as well (as many as last time + 15 %: the ghost counts drift by a per
+    // cent per Lloyd step, and growing a GB-sized buffer in the middle of a run costs 100+ ms)
+    const size_t want = size_t(nx) + size_t(S->st.n_ghost_yz) + (size_t(nx) + S->st.n_ghost_yz) / 7 + 4096;
+    if((rc = c->xyz.reserve(3 * want)) || (rc = S->lgid.reserve(want)) || (rc = S->ltc.reserve(want)) ||
+       (S->has_w && (rc = c->wgt.reserve(want)))) {
         return rc;
     }
     assemble_kernel<<<(nx + 255) / 256, 256, 0, st>>>(n_own, nrecv, S->own.p, S->has_w ? S->own_w.p : nullptr,

@@ -219,6 +219,7 @@ class SlabLloyd(object):
         self._comm_ms = 0.0
         self.retries = 0
         self.last_stats = None
+        self.steps = []          # per step: device ms of exchange / pack / grid / clip, ghosts, retries
 
     def set_seeds_device(self, full, slabs=True):
         """full: (n_total,3) float64 device tensor of ALL seeds, identical on every rank (set-up
@@ -243,6 +244,8 @@ class SlabLloyd(object):
         self.phase["ms_clip"] += s["ms_clip"]
         self._comm_ms += s["ms_exchange"] + s["ms_pack"]
         self.retries += s["retries"]
+        self.steps.append({k: (round(s[k], 3) if isinstance(s[k], float) else s[k])
+                           for k in ("ms_exchange", "ms_pack", "ms_grid", "ms_clip", "n_local", "retries")})
 
     def get_shard_host(self, host_rows):
         self.ctx.slab_lloyd_device(0, self.mine.data_ptr())
