@@ -73,3 +73,20 @@ def test_host_cpp_on_gpu():
     print(p.stdout[-2000:], p.stderr[-2000:])
     assert p.returncode == 0
     assert "host test: ok" in p.stdout
+
+
+@pytest.mark.gpu
+def test_host_cpp_slab_lloyd_two_processes(tmp_path):
+    """Multi-GPU Lloyd driven from plain C++ (b200vor_comm_init + b200vor_slab_*, no torch, no MPI):
+    two processes, one GPU each, the NCCL id handed over through a file; every rank's rows must equal
+    the single-context run.  Needs two GPUs (skipped on a one-GPU box; run with gpurun --gpus 2)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    exe = os.path.join(LIB, "test_host_slab")
+    idf = str(tmp_path / "nccl_id")
+    procs = [subprocess.Popen([exe, str(r), "2", idf], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+             for r in range(2)]
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0 and "host slab test: ok" in o, o[-2000:]
