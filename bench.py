@@ -466,11 +466,13 @@ def main():
         del raw_rows
         torch.cuda.synchronize()
 
+        bufs = [host_in, host_out]
+
         def e2e_step():
-            job.set_shard_host(host_in)
+            job.set_shard_host(bufs[0])
             job.step(k0=args.k0, mode=args.mode)
-            job.get_shard_host(host_out)
-            host_in.copy_(host_out)      # the next iteration starts from this one's result
+            job.get_shard_host(bufs[1])
+            bufs.reverse()               # the next iteration starts from this one's result (no host copy)
 
         barrier()
         t0 = time.perf_counter()
