@@ -12,6 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("B200VOR_LIB") or os.path.join(_HERE, "lib", "libb200vor.so")
 
 BOX_ID = 0xFFFFFFF0
+DOMAIN_ID = 0xFFFFFF00
 CELL_OK = 0
 CELL_UNCERTIFIED = 1
 CELL_UNCERTAIN = 2
@@ -25,7 +26,7 @@ FCAP = 64
 # every symbol include/b200vor.h declares
 EXPORTS = [
     "b200vor_version", "b200vor_last_error", "b200vor_create", "b200vor_destroy",
-    "b200vor_set_domain_box", "b200vor_set_domain_periodic", "b200vor_set_points",
+    "b200vor_set_domain_box", "b200vor_set_domain_periodic", "b200vor_set_domain_planes", "b200vor_set_points",
     "b200vor_knn", "b200vor_knn_points", "b200vor_compute_cells", "b200vor_get_cells",
     "b200vor_get_faces", "b200vor_get_vertices", "b200vor_get_cvt", "b200vor_otm_newton", "b200vor_get_spatial_order", "b200vor_lloyd", "b200vor_get_stats",
     "b200vor_set_points_per_cell", "b200vor_set_stream", "b200vor_set_query_range",
@@ -124,6 +125,7 @@ def load_library():
     lib.b200vor_destroy.restype = None
     lib.b200vor_set_domain_box.argtypes = [vp, vp]
     lib.b200vor_set_domain_periodic.argtypes = [vp, dbl]
+    lib.b200vor_set_domain_planes.argtypes = [vp, u32, vp]
     lib.b200vor_set_points.argtypes = [vp, u32, vp, u32, vp, i32]
     lib.b200vor_knn.argtypes = [vp, u32, vp, vp, i32]
     lib.b200vor_knn_points.argtypes = [vp, u32, vp, u32, vp, vp, i32]
@@ -192,6 +194,12 @@ class Context(object):
     def set_domain_box(self, box):
         box = np.ascontiguousarray(box, np.float64)
         self._check(self.lib.b200vor_set_domain_box(self.h, _ptr(box)))
+
+    def set_domain_planes(self, planes):
+        """planes: (k,4) rows a, b, c, d of the half-spaces a x + b y + c z + d >= 0 of a convex domain
+        (k <= 32; None or empty removes them); box domains only"""
+        pl = np.zeros((0, 4)) if planes is None else np.ascontiguousarray(planes, np.float64).reshape(-1, 4)
+        self._check(self.lib.b200vor_set_domain_planes(self.h, pl.shape[0], _ptr(pl) if pl.shape[0] else None))
 
     def set_domain_periodic(self, period=1.0):
         self._check(self.lib.b200vor_set_domain_periodic(self.h, float(period)))

@@ -148,6 +148,10 @@ int cells_pipeline(Ctx* c, const b200vor_cell_params* params, bool collect_event
         set_error("b200vor_compute_cells: no points");
         return B200VOR_ERR_ARG;
     }
+    if(c->ndom > 0 && p.mode == 2) {
+        set_error("b200vor_compute_cells: the kNN-table pipeline (mode 2) knows no domain planes");
+        return B200VOR_ERR_ARG;
+    }
     const uint32_t n = c->n;
     const uint64_t ntotal = c->periodic ? 27ull * n : n;
     // row length: k neighbours + the seed itself at rank 0
@@ -308,7 +312,7 @@ int cells_pipeline(Ctx* c, const b200vor_cell_params* params, bool collect_event
     // (the kNN-table fallback knows nothing of open faces: on a slab-local grid the flags stay)
     // (nor can a table of <= kmax neighbours certify the far-reaching cells of clustered seeds that
     //  the large-cell instance gave up on: their flags stay too)
-    for(int pass = pass0; pass < 8 && nq > 0 && !c->open && !far_sweep; ++pass) {
+    for(int pass = pass0; pass < 8 && nq > 0 && !c->open && !far_sweep && c->ndom == 0; ++pass) {
         uint32_t rl = row_len(k);
         if((rc = c->knn.reserve(size_t(nq) * rl)) || (rc = c->knn_flag.reserve(nq))) {
             return rc;
@@ -487,7 +491,7 @@ void b200vor_destroy(b200vor_ctx* h) {
     cudaStreamSynchronize(c.stream);
     slab_release(&c);
     c.xyz.release(); c.wgt.release(); c.cellid.release(); c.rank.release();
-    c.sub.release(); c.vstart.release(); c.vcount.release(); c.sbcount.release(); c.wloc.release(); c.wloc_tmp.release();
+    c.sub.release(); c.vstart.release(); c.vcount.release(); c.sbcount.release(); c.dom_dev.release(); c.wloc.release(); c.wloc_tmp.release();
     c.cell_start.release(); c.perm.release(); c.scan_tmp.release(); c.sorted.release();
     c.knn.release(); c.knn_flag.release(); c.qlist.release(); c.qlist2.release(); c.qlist3.release(); c.qrows.release();
     c.counter.release(); c.m.release(); c.mg.release(); c.status.release();
@@ -517,6 +521,37 @@ int b200vor_set_domain_box(b200vor_ctx* h, const double* box) {
     return B200VOR_OK;
 }
 
+int b200vor_set_domain_planes(b200vor_ctx* h, uint32_t n, const double* planes) {
+    if(!h || n > 32 || (n > 0 && !planes)) {
+        set_error("b200vor_set_domain_planes: invalid argument (at most 32 planes)");
+        return B200VOR_ERR_ARG;
+    }
+    Ctx* c = &h->c;
+    if(n > 0 && c->periodic) {
+        set_error("b200vor_set_domain_planes: box domains only");
+        return B200VOR_ERR_ARG;
+    }
+    B200_CUDA_CHECK(cudaSetDevice(c->device));
+    for(uint32_t k = 0; k < n; ++k) {
+        const double* p = planes + 4 * size_t(k);
+        if(!(p[0] * p[0] + p[1] * p[1] + p[2] * p[2] > 0.0)) {
+            set_error("b200vor_set_domain_planes: plane %u has no normal", k);
+            return B200VOR_ERR_ARG;
+        }
+    }
+    int rc;
+    if(n > 0) {
+        if((rc = c->dom_dev.reserve(4 * size_t(n)))) {
+            return rc;
+        }
+        B200_CUDA_CHECK(cudaMemcpyAsync(c->dom_dev.p, planes, 4 * size_t(n) * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        B200_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    }
+    c->ndom = int(n);
+    c->cells_valid = c->faces_valid = false;
+    return B200VOR_OK;
+}
+
 int b200vor_set_domain_periodic(b200vor_ctx* h, double period) {
     if(!h || !(period > 0.0)) {
         set_error("b200vor_set_domain_periodic: invalid argument");
@@ -525,6 +560,10 @@ int b200vor_set_domain_periodic(b200vor_ctx* h, double period) {
     if(uint64_t(h->c.n) * 27ull >= 0xFFFFFFF0ull) {
         // the points were set first: the same check as in b200vor_set_points
         set_error("b200vor_set_domain_periodic: n too large for 32-bit periodic ids");
+        return B200VOR_ERR_ARG;
+    }
+    if(h->c.ndom > 0) {
+        set_error("b200vor_set_domain_periodic: remove the domain planes first (b200vor_set_domain_planes(ctx, 0, NULL))");
         return B200VOR_ERR_ARG;
     }
     slab_deactivate(&h->c);

@@ -78,6 +78,8 @@ struct Ctx {
     double ppc = 8.0;
     int fused_sweep_mode = 0;      // (pipeline -> fused.cu) large-cell instance: 0 sweep in bands x4, 1 bands x1.25, 2 no sweep
     bool fused_bail_far = false;   // (pipeline -> fused.cu) far-reaching cells go straight to the large-cell instance
+    int ndom = 0;              // planes of the convex domain (b200vor_set_domain_planes), clipped before any neighbour
+    DevBuf<double> dom_dev;
     int open = 0;              // slab-local context: open faces of the local grid (GridDesc::open)
     struct Slab* slab = nullptr;   // multi-GPU slab state (slab.cu), or NULL
 

@@ -67,7 +67,7 @@ __global__ void otm_coef_kernel(uint32_t n, const double* __restrict__ xyz, int 
         double cf = 0.0;
         if(f < nf) {
             const uint32_t id = face_nbr[size_t(r) * kFcap + f];
-            if(id < B200VOR_BOX_ID) {
+            if(id < B200VOR_DOMAIN_ID) {   // (not a face on the clipping box or on a plane of the convex domain)
                 j = id % n;
                 const uint32_t inst = id / n;
                 int tx = 0, ty = 0, tz = 0;

@@ -475,7 +475,7 @@ __global__ void remap_faces_kernel(uint32_t n_own, uint32_t fcap, const uint32_t
     double* ar = face_area + size_t(i) * fcap;
     for(uint32_t k = 0; k < nf; ++k) {
         const uint32_t j = ids[k];
-        if(j < B200VOR_BOX_ID) {
+        if(j < B200VOR_DOMAIN_ID) {
             uint32_t inst = 0;
             if(periodic) {
                 // translation of the neighbour RELATIVE to the image the cell's own seed is kept at

@@ -79,7 +79,7 @@ int exact_sign_selftest(Ctx* c, uint32_t n, const double* planes_host, int* out_
 // can the thread-per-cell kernel take the cells of this context?  (unweighted, single-level grid,
 // at least a 3x3x3 block of bins on a periodic domain, ids that fit 27 bits)
 bool tpc_applicable(const Ctx* c) {
-    if(c->has_w || c->grid.two_level || c->n >= (1u << 27) || c->open) {
+    if(c->has_w || c->grid.two_level || c->n >= (1u << 27) || c->open || c->ndom) {
         return false;   // (a slab-local grid with open faces is walked by the team kernel only)
     }
     if(c->periodic) {

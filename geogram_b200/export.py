@@ -20,6 +20,7 @@ the device.
 import numpy as np
 
 BOX_ID = 0xFFFFFFF0
+DOMAIN_ID = 0xFFFFFF00
 NOT_AVAILABLE = 0xFFFFFFFF
 
 
@@ -175,7 +176,7 @@ def delaunay_tets(nverts, vert_faces, nfaces, face_nbr, n, xyz=None, period=0.0)
     rows = np.nonzero(valid)
     f = vert_faces[rows].astype(np.int64)                     # (K, 3) face positions
     nb = face_nbr[rows[0][:, None], f].astype(np.int64)       # (K, 3) neighbour ids
-    interior = (nb < BOX_ID).all(axis=1)
+    interior = (nb < DOMAIN_ID).all(axis=1)    # no face on the box or on a plane of the convex domain
     seed = rows[0][interior]
     nb = nb[interior]
     keep = (seed[:, None] < (nb % n)).all(axis=1)

@@ -365,7 +365,7 @@ index_t ConvexCellBatch::delaunay_tetrahedra(std::vector<global_index_t>& tets) 
             bool keep = true;
             for(index_t l = 0; l < 3 && keep; ++l) {
                 v[l] = v_global_index(c, triangle_v_local_index(c, t, l));
-                keep = v[l] < BOX_ID && c < v[l] % n;   // reported by the smallest real index
+                keep = v[l] < DOMAIN_ID && c < v[l] % n;   // reported by the smallest real index
             }
             if(keep) {
                 tets.push_back(c);

@@ -42,6 +42,8 @@ struct vec3 {
 
 /* ids >= BOX_ID in face lists are the six planes of the clipping box (x-,x+,y-,y+,z-,z+) */
 const global_index_t BOX_ID = 0xFFFFFFF0u;
+/* ids in [DOMAIN_ID, BOX_ID) are planes of a convex domain (b200vor_set_domain_planes) */
+const global_index_t DOMAIN_ID = 0xFFFFFF00u;
 
 class NearestNeighborSearch {
 public:

@@ -120,6 +120,14 @@ int  b200vor_version(void);
 /* ---- domain ---- */
 /* cells are clipped by box = {xmin,ymin,zmin,xmax,ymax,zmax} (default: unit cube) */
 int b200vor_set_domain_box(b200vor_ctx* ctx, const double* box);
+/* convex polyhedral domain: every cell is also clipped by the n half-spaces a x + b y + c z + d >= 0
+ * (planes: 4 doubles each, host memory; n <= 32; n = 0 removes them), before any neighbour -- what
+ * VBW::ConvexCell::clip_by_plane does for one convex region of a restricted Voronoi diagram
+ * (voronoi/convex_cell.cpp:467-516; first slice of the mesh-restricted cells of voronoi/generic_RVD.h:1464-1597).
+ * Box domains only; a face on plane k is reported as neighbour id B200VOR_DOMAIN_ID + k.  Cells are computed
+ * by the team kernels only (a cell beyond their capacities keeps its flag). */
+#define B200VOR_DOMAIN_ID 0xFFFFFF00u
+int b200vor_set_domain_planes(b200vor_ctx* ctx, uint32_t n, const double* planes);
 /* periodic cube [0,period)^3; neighbour ids become real + n*instance (periodic.h:95-99) */
 int b200vor_set_domain_periodic(b200vor_ctx* ctx, double period);
 

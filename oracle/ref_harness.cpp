@@ -366,6 +366,14 @@ uint32_t georef_delaunay_tets(uint32_t n, const double* xyz, uint32_t* tets, uin
  * of uncertified cells; stats[5] = total kNN rounds.
  * times[0] = kd-tree build, times[1] = everything else.
  */
+/* convex domain for georef_cells_knn: planes a x + b y + c z + d >= 0 clipped by the reference's own
+ * ConvexCell::clip_by_plane right after init_with_box; face id of plane k = DOMAIN_ID + k */
+static std::vector<double> g_domain;
+static const GEO::index_t DOMAIN_ID = 0xFFFFFF00u;
+void georef_set_domain_planes(uint32_t n, const double* planes) {
+    g_domain.assign(planes, planes + 4 * size_t(n));
+}
+
 int georef_cells_knn(
     uint32_t n, const double* xyz, const double* w, const double* box,
     uint32_t k0, uint32_t kcap, int exact_predicates,
@@ -402,6 +410,10 @@ int georef_cells_knn(
                 C.init_with_box(box[0], box[1], box[2], box[3], box[4], box[5]);
                 for(VBW::index_t lv = 1; lv <= 6; ++lv) {
                     C.set_v_global_index(lv, BOX_ID + (lv - 1));
+                }
+                for(size_t kd = 0; kd < g_domain.size() / 4; ++kd) {
+                    C.clip_by_plane(VBW::make_vec4(g_domain[4 * kd], g_domain[4 * kd + 1], g_domain[4 * kd + 2],
+                                                   g_domain[4 * kd + 3]), DOMAIN_ID + GEO::index_t(kd));
                 }
                 uint32_t k = std::min(k0, kcap);
                 uint32_t jj = 1;       // rank 0 is the seed itself

@@ -606,6 +606,12 @@ int n_threads() {
 
 extern "C" {
 
+/* convex domain (b200vor_set_domain_planes): cells are clipped by these planes before any neighbour
+ * (ConvexCell::clip_by_plane, convex_cell.cpp:467-516); a face on plane k gets the id VO_DOMAIN_ID + k */
+static std::vector<double> g_domain;
+void vo_set_domain_planes(uint32_t n, const double* planes) {
+    g_domain.assign(planes, planes + 4 * size_t(n));
+}
 void vo_set_num_threads(int nthreads) { g_threads = nthreads; }
 void vo_set_energy_output(double* energy) { g_energy = energy; }
 int vo_num_threads(void) { return n_threads(); }
@@ -689,6 +695,12 @@ int vo_cells(uint32_t n, const double* xyz, const double* w, int periodic,
                 std::memcpy(bx, box, sizeof(bx));
             }
             C.init_box(bx);
+            if(!periodic) {
+                for(size_t kd = 0; kd < g_domain.size() / 4; ++kd) {
+                    Plane4 D = {g_domain[4 * kd], g_domain[4 * kd + 1], g_domain[4 * kd + 2], g_domain[4 * kd + 3]};
+                    C.clip(D, 0xFFFFFF00u + uint32_t(kd));
+                }
+            }
             C.nP = C.nC = C.nV = 0;
             uint32_t k = std::min(std::max(k0, 1u), kcap), jj = 1;
             bool certified = false;

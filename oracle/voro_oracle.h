@@ -62,6 +62,8 @@ int vo_cells(uint32_t n, const double* xyz, const double* w,
  * every cell, the integral of |x - seed_i|^2 over the cell (the per-cell share of f in
  * ComputeCVTFuncGradVolumetric, voronoi/RVD.cpp:791-876).  NULL switches it off. */
 void vo_set_energy_output(double* energy);
+/* convex domain: n planes (4 doubles each, a x + b y + c z + d >= 0 inside) clipped before any neighbour on box domains; n = 0 removes them */
+void vo_set_domain_planes(uint32_t n, const double* planes);
 
 /* One Lloyd update: xyz_out = mg/m where m > 1e-30, else unchanged; periodic wrap. */
 int vo_lloyd_update(uint32_t n, const double* xyz, const double* m, const double* mg,

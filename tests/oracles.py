@@ -19,6 +19,7 @@ PORT_SO = os.path.join(ROOT, "oracle", "_build", "libvoro_oracle.so")
 REF_SO = os.path.join(ROOT, "oracle", "_ref", "libgeoref.so")
 
 BOX_ID = 0xFFFFFFF0
+DOMAIN_ID = 0xFFFFFF00
 UNCERTIFIED = 0xFFFFFFFF
 UNIT_BOX = np.array([0.0, 0.0, 0.0, 1.0, 1.0, 1.0])
 
@@ -91,9 +92,12 @@ class Port(object):
         return nbr, d2
 
     def cells(self, xyz, w=None, periodic=False, period=1.0, box=UNIT_BOX,
-              k0=20, kcap=1000, fcap=64, areas=False, energy=False):
+              k0=20, kcap=1000, fcap=64, areas=False, energy=False, domain=None):
+        """domain: optional (k,4) planes a x + b y + c z + d >= 0 of a convex domain (box domains)"""
         xyz = np.ascontiguousarray(xyz, np.float64)
         n = xyz.shape[0]
+        dom = np.zeros((0, 4)) if domain is None else np.ascontiguousarray(domain, np.float64)
+        self.lib.vo_set_domain_planes(ctypes.c_uint32(dom.shape[0]), _p(dom, _cd) if dom.shape[0] else None)
         if w is not None:
             w = np.ascontiguousarray(w, np.float64)
         box = np.ascontiguousarray(box, np.float64)
@@ -107,6 +111,7 @@ class Port(object):
             _p(R.face_nbr, _cu), _p(R.face_area, _cd), ctypes.c_uint32(fcap),
             _p(R.kstop, _cu), _p(R.flags, _cu), _p(R.stats, _cd))
         self.lib.vo_set_energy_output(None)
+        self.lib.vo_set_domain_planes(ctypes.c_uint32(0), None)
         assert r == 0
         return R
 
@@ -186,10 +191,13 @@ class Reference(object):
         return tets[:cnt]
 
     def cells_knn(self, xyz, w=None, box=UNIT_BOX, k0=20, kcap=1000, exact=True,
-                  fcap=64, areas=False):
-        """Oracle B."""
+                  fcap=64, areas=False, domain=None):
+        """Oracle B.  domain: optional (k,4) planes of a convex domain, clipped by the reference's own
+        ConvexCell::clip_by_plane before any neighbour."""
         xyz = np.ascontiguousarray(xyz, np.float64)
         n = xyz.shape[0]
+        dom = np.zeros((0, 4)) if domain is None else np.ascontiguousarray(domain, np.float64)
+        self.lib.georef_set_domain_planes(ctypes.c_uint32(dom.shape[0]), _p(dom, _cd) if dom.shape[0] else None)
         if w is not None:
             w = np.ascontiguousarray(w, np.float64)
         box = np.ascontiguousarray(box, np.float64)
@@ -199,6 +207,7 @@ class Reference(object):
             ctypes.c_uint32(k0), ctypes.c_uint32(kcap), int(exact), _p(R.m, _cd),
             _p(R.mg, _cd), _p(R.nfaces, _cu), _p(R.face_nbr, _cu), _p(R.face_area, _cd),
             ctypes.c_uint32(fcap), _p(R.kstop, _cu), _p(R.stats, _cd), _p(R.times, _cd))
+        self.lib.georef_set_domain_planes(ctypes.c_uint32(0), None)
         assert r == 0
         return R
 

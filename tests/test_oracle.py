@@ -132,3 +132,30 @@ def test_port_vs_reference_live(port, reference):
     Rp = port.cells(xyz, periodic=True)
     assert oracles.face_mismatches(Rp, Ap) == 0
     assert np.all(np.abs(Rp.m - Ap.m) <= VOL_RTOL * Ap.m)
+
+
+def _convex_domain():
+    """a convex polyhedron inside the unit box: the box cut by four oblique planes (rows a, b, c, d of
+    a x + b y + c z + d >= 0)"""
+    return np.array([[-1.0, -1.0, -1.0, 2.1],       # x + y + z <= 2.1
+                     [1.0, -1.0, 0.0, 0.6],         # y - x <= 0.6
+                     [0.3, 0.2, 1.0, -0.23],        # 0.3 x + 0.2 y + z >= 0.23 (no plane through a corner of the box)
+                     [0.0, 1.0, -0.5, 0.35]])       # y - 0.5 z >= -0.35
+
+
+def test_port_convex_domain_vs_reference(port, reference):
+    """Cells clipped by a convex polyhedral domain (the planes go through ConvexCell::clip_by_plane right
+    after init_with_box, convex_cell.cpp:467-516): the port against the unmodified reference (oracle B)."""
+    xyz = oracles.uniform_seeds(4000, 21)
+    dom = _convex_domain()
+    A = reference.cells_knn(xyz, domain=dom, areas=True)
+    B = port.cells(xyz, domain=dom, areas=True)
+    assert oracles.face_mismatches(A, B) == 0
+    inside = A.m > 0
+    assert inside.sum() > 2000 and (~inside).sum() > 200          # seeds outside the domain own nothing (or a sliver)
+    assert np.abs(A.m - B.m).max() < 1e-12
+    # the cells tile the domain: its volume from a fine Monte-Carlo-free formula = sum of the reference cells
+    assert abs(A.m.sum() - B.m.sum()) < 1e-12
+    # faces on domain planes carry the domain ids
+    ids = A.face_nbr[np.arange(64)[None, :] < A.nfaces[:, None]]
+    assert ((ids >= oracles.DOMAIN_ID) & (ids < oracles.DOMAIN_ID + 4)).sum() > 100
