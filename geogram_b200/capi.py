@@ -28,7 +28,7 @@ EXPORTS = [
     "b200vor_version", "b200vor_last_error", "b200vor_create", "b200vor_destroy",
     "b200vor_set_domain_box", "b200vor_set_domain_periodic", "b200vor_set_domain_planes", "b200vor_set_points",
     "b200vor_knn", "b200vor_knn_points", "b200vor_compute_cells", "b200vor_get_cells",
-    "b200vor_get_faces", "b200vor_get_vertices", "b200vor_get_cvt", "b200vor_otm_newton", "b200vor_get_spatial_order", "b200vor_lloyd", "b200vor_get_stats",
+    "b200vor_get_faces", "b200vor_get_vertices", "b200vor_get_cvt", "b200vor_otm_newton", "b200vor_get_spatial_order", "b200vor_get_hilbert_order", "b200vor_lloyd", "b200vor_get_stats",
     "b200vor_set_points_per_cell", "b200vor_set_stream", "b200vor_set_query_range",
     "b200vor_microbench", "b200vor_selftest_exact_sign",
     "b200vor_comm_unique_id", "b200vor_comm_init", "b200vor_slab_set_halo_bins", "b200vor_slab_set_points",
@@ -136,6 +136,7 @@ def load_library():
     lib.b200vor_get_cvt.argtypes = [vp, vp, vp, ctypes.POINTER(dbl), i32]
     lib.b200vor_otm_newton.argtypes = [vp, vp, vp, ctypes.POINTER(OtmParams), ctypes.POINTER(OtmResult), i32]
     lib.b200vor_get_spatial_order.argtypes = [vp, vp, i32]
+    lib.b200vor_get_hilbert_order.argtypes = [vp, vp, i32]
     lib.b200vor_lloyd.argtypes = [vp, u32, ctypes.POINTER(CellParams), vp, i32]
     lib.b200vor_get_stats.argtypes = [vp, ctypes.POINTER(Stats)]
     lib.b200vor_set_points_per_cell.argtypes = [vp, dbl]
@@ -288,6 +289,12 @@ class Context(object):
         """permutation of the seeds in grid order (spatial sort; role of compute_Hilbert_order)"""
         order = np.zeros(self.n, np.uint32)
         self._check(self.lib.b200vor_get_spatial_order(self.h, _ptr(order), 0))
+        return order
+
+    def hilbert_order(self):
+        """permutation of the seeds along the Hilbert curve of the grid (bin by bin, inside a bin by index)"""
+        order = np.zeros(self.n, np.uint32)
+        self._check(self.lib.b200vor_get_hilbert_order(self.h, _ptr(order), 0))
         return order
 
     def get_cvt(self):

@@ -975,6 +975,38 @@ int b200vor_get_spatial_order(b200vor_ctx* h, uint32_t* order, int on_device) {
     return B200VOR_OK;
 }
 
+int b200vor_get_hilbert_order(b200vor_ctx* h, uint32_t* order, int on_device) {
+    if(!h || !order || h->c.n == 0) {
+        set_error("b200vor_get_hilbert_order: needs a context with points and an output array");
+        return B200VOR_ERR_ARG;
+    }
+    Ctx* c = &h->c;
+    B200_CUDA_CHECK(cudaSetDevice(c->device));
+    int rc;
+    if(c->grid_dirty && (rc = ensure_grid(c))) {
+        return rc;
+    }
+    uint32_t* dst = order;
+    if(!on_device) {
+        if((rc = c->out_nbr.reserve(c->n))) {
+            return rc;
+        }
+        dst = c->out_nbr.p;
+    }
+    rc = hilbert_order(c, dst);
+    if(rc == 1) {
+        // a grid too elongated for the curve enumeration: the raster order of the bins
+        B200_CUDA_CHECK(cudaMemcpyAsync(dst, c->perm.p, size_t(c->n) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
+    } else if(rc) {
+        return rc;
+    }
+    if(!on_device && (rc = copy_out(order, dst, size_t(c->n) * sizeof(uint32_t), 0, c->stream))) {
+        return rc;
+    }
+    B200_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return B200VOR_OK;
+}
+
 int b200vor_selftest_exact_sign(b200vor_ctx* h, uint32_t n, const double* planes, int* signs) {
     if(!h || !planes || !signs || n == 0) {
         set_error("b200vor_selftest_exact_sign: invalid argument");

@@ -130,6 +130,7 @@ struct Ctx {
 
 // grid.cu
 int build_grid(Ctx* c);
+int hilbert_order(Ctx* c, uint32_t* order_dev);   // 1 = grid too elongated (caller falls back to the raster order)
 // knn.cu
 struct KnnJob {
     uint32_t nq;

@@ -315,6 +315,78 @@ __global__ void superbin_count_kernel(GridDesc G, const uint32_t* __restrict__ c
     atomicAdd(&sbcount[(ix >> kSuperLog) + sx * ((iy >> kSuperLog) + sy * (iz >> kSuperLog))], cnt);
 }
 
+// ---- Hilbert order of the bins (role of compute_Hilbert_order, mesh/mesh_reorder.cpp:1260-1300) ----
+// cell (x, y, z) of the 2^b cube at position h of the 3-D Hilbert curve (Skilling's transpose form)
+__device__ inline void hilbert_decode(uint32_t h, int b, uint32_t& x, uint32_t& y, uint32_t& z) {
+    uint32_t X[3] = {0u, 0u, 0u};
+    for(int i = 0; i < b; ++i) {
+        X[0] |= ((h >> (3 * i + 2)) & 1u) << i;
+        X[1] |= ((h >> (3 * i + 1)) & 1u) << i;
+        X[2] |= ((h >> (3 * i)) & 1u) << i;
+    }
+    const uint32_t N = 2u << (b - 1);
+    uint32_t t = X[2] >> 1;
+    X[2] ^= X[1];
+    X[1] ^= X[0];
+    X[0] ^= t;
+    for(uint32_t Q = 2; Q != N; Q <<= 1) {
+        const uint32_t P = Q - 1;
+        for(int i = 2; i >= 0; --i) {
+            if(X[i] & Q) {
+                X[0] ^= P;
+            } else {
+                t = (X[0] ^ X[i]) & P;
+                X[0] ^= t;
+                X[i] ^= t;
+            }
+        }
+    }
+    x = X[0]; y = X[1]; z = X[2];
+}
+
+// The g bins of an axis are spread evenly over the 2^b cells of the cube axis (bin x sits in cell
+// floor(x 2^b / g)), so the curve never leaves the grid for long: the bin of cube cell X, or -1.
+__device__ inline int cube_to_bin(uint32_t X, int g, int b) {
+    const uint32_t x = uint32_t((uint64_t(X) * uint32_t(g) + ((1u << b) - 1u)) >> b);   // ceil(X g / 2^b)
+    return (x < uint32_t(g) && uint32_t((uint64_t(x) << b) / uint32_t(g)) == X) ? int(x) : -1;
+}
+
+// seeds of the bin at curve position h (0 if the cube cell holds no bin)
+__global__ void hilbert_count_kernel(GridDesc G, int b, uint32_t nh, const uint32_t* __restrict__ cell_start,
+                                     uint32_t* __restrict__ cnt) {
+    const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
+    if(h >= nh) {
+        return;
+    }
+    uint32_t x, y, z, c = 0;
+    hilbert_decode(h, b, x, y, z);
+    const int bx = cube_to_bin(x, G.g[0], b), by = cube_to_bin(y, G.g[1], b), bz = cube_to_bin(z, G.g[2], b);
+    if(bx >= 0 && by >= 0 && bz >= 0) {
+        const uint32_t bin = uint32_t(bx) + uint32_t(G.g[0]) * (uint32_t(by) + uint32_t(G.g[1]) * uint32_t(bz));
+        c = cell_start[bin + 1] - cell_start[bin];
+    }
+    cnt[h] = c;
+}
+
+__global__ void hilbert_emit_kernel(GridDesc G, int b, uint32_t nh, const uint32_t* __restrict__ cell_start,
+                                    const uint32_t* __restrict__ off, const uint32_t* __restrict__ perm,
+                                    uint32_t* __restrict__ order) {
+    const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
+    if(h >= nh) {
+        return;
+    }
+    uint32_t x, y, z;
+    hilbert_decode(h, b, x, y, z);
+    const int bx = cube_to_bin(x, G.g[0], b), by = cube_to_bin(y, G.g[1], b), bz = cube_to_bin(z, G.g[2], b);
+    if(bx >= 0 && by >= 0 && bz >= 0) {
+        const uint32_t bin = uint32_t(bx) + uint32_t(G.g[0]) * (uint32_t(by) + uint32_t(G.g[1]) * uint32_t(bz));
+        const uint32_t a = cell_start[bin], e = cell_start[bin + 1];
+        for(uint32_t k = a; k < e; ++k) {
+            order[off[h] + (k - a)] = perm[k];
+        }
+    }
+}
+
 // ---- local weight bound (Laguerre cells): wloc[b] = max weight of the seeds in the bins within
 //      Chebyshev distance kWlocRing of bin b; lets the security radius use a LOCAL weight spread
 //      (fused_kernel.inc, sr_bound) when the weights vary smoothly over the domain ----
@@ -362,6 +434,39 @@ __global__ void dilate_max_kernel(GridDesc G, int axis, int ring, const double* 
 }
 
 }  // namespace
+
+// order[n] (device): the seeds bin by bin ALONG THE HILBERT CURVE of the grid, inside a bin by index.
+// No sort: the curve positions are enumerated (8^b of them, b = bits of the largest grid side), the
+// bins inside the grid counted, scanned and emitted.  Returns 1 if the grid is too elongated for that
+// (8^b > 2^27): the caller falls back to the raster order.
+int hilbert_order(Ctx* c, uint32_t* order_dev) {
+    const GridDesc& G = c->grid;
+    int b = 1;
+    while((1 << b) < std::max(G.g[0], std::max(G.g[1], G.g[2]))) {
+        ++b;
+    }
+    if(3 * b > 27) {
+        return 1;
+    }
+    const uint32_t nh = 1u << (3 * b);
+    const uint32_t ntiles = (nh + kScanTile - 1) / kScanTile;
+    int rc;
+    if((rc = c->scan_tmp.reserve(size_t(ntiles) + 2 * size_t(nh) + 128))) {
+        return rc;
+    }
+    uint32_t* tile_sums = c->scan_tmp.p;
+    uint32_t* cnt = c->scan_tmp.p + ntiles + 1;
+    uint32_t* off = cnt + nh;
+    cudaStream_t st = c->stream;
+    hilbert_count_kernel<<<(nh + kThreads - 1) / kThreads, kThreads, 0, st>>>(G, b, nh, c->cell_start.p, cnt);
+    scan_tile_sums<<<ntiles, kThreads, 0, st>>>(cnt, nh, tile_sums);
+    scan_of_sums<<<1, kThreads, 0, st>>>(tile_sums, ntiles);
+    scan_apply<<<ntiles, kThreads, 0, st>>>(cnt, nh, tile_sums, off, c->n);   // (also writes off[nh] = n)
+    hilbert_emit_kernel<<<(nh + kThreads - 1) / kThreads, kThreads, 0, st>>>(G, b, nh, c->cell_start.p, off, c->perm.p, order_dev);
+    c->stats.gpu_launches += 5;
+    B200_CUDA_CHECK(cudaGetLastError());
+    return B200VOR_OK;
+}
 
 int build_wloc(Ctx* c) {
     // two fields: a tight one (kWlocRingNear bins) and a wide one (kWlocRingFar bins); a cell uses

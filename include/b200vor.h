@@ -33,7 +33,8 @@
  *   b200vor_get_cvt          ComputeCVTFuncGradVolumetric (f, g)    voronoi/RVD.cpp:791-876
  *   b200vor_otm_newton       [external] OptimalTransportMap3d::optimize (exploragram; call sites
  *                            src/examples/exploragram/compute_OTM/main.cpp:284-297)
- *   b200vor_get_spatial_order  compute_Hilbert_order (role)         mesh/mesh_reorder.cpp:1260-1300
+ *   b200vor_get_spatial_order, b200vor_get_hilbert_order
+ *                            compute_Hilbert_order (role)           mesh/mesh_reorder.cpp:1260-1300
  *   b200vor_lloyd            CentroidalVoronoiTesselation::Lloyd_iterations
  *                                                                   voronoi/CVT.cpp:133-169
  */
@@ -220,6 +221,12 @@ int b200vor_set_query_range(b200vor_ctx* ctx, uint32_t first, uint32_t last);
  * pre-ordering (mesh/mesh_reorder.cpp:1260-1300, compute_Hilbert_order): consecutive entries are
  * neighbours in space.  Available after b200vor_set_points. */
 int b200vor_get_spatial_order(b200vor_ctx* ctx, uint32_t* order, int on_device);
+/* order[n]: the same bins visited ALONG THE 3-D HILBERT CURVE of the grid (inside a bin by index): no jump
+ * at the end of a row of bins -- consecutive entries are in adjacent or next-to-adjacent bins (the g bins
+ * of an axis are spread over the 2^b cells of the curve's cube).  compute_Hilbert_order (mesh/mesh_reorder.cpp:1260-1300) sorts by recursive median
+ * splits; this is the curve of the uniform grid, same role (locality of a point order), not the same
+ * permutation. */
+int b200vor_get_hilbert_order(b200vor_ctx* ctx, uint32_t* order, int on_device);
 
 /* ---- introspection ---- */
 int b200vor_get_stats(b200vor_ctx* ctx, b200vor_stats* stats);

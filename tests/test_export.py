@@ -177,3 +177,30 @@ def oracles_translations():
                 i = (tz + 1) + 3 * (ty + 1) + 9 * (tx + 1)
                 T[0 if i == 13 else (i + 1 if i < 13 else i)] = (tx, ty, tz)
     return T
+
+
+@pytest.mark.gpu
+def test_hilbert_order_is_a_local_permutation():
+    """b200vor_get_hilbert_order (role of compute_Hilbert_order, mesh/mesh_reorder.cpp:1260-1300): a
+    permutation of the seeds in which consecutive entries are spatial neighbours EVERYWHERE -- the raster
+    order of the grid jumps across the domain at the end of every row of bins, the curve never does."""
+    import oracles
+    from geogram_b200 import Context
+    n = 200000
+    xyz = oracles.uniform_seeds(n, 17)
+    ctx = Context(0)
+    ctx.set_points(xyz)
+    h = ctx.hilbert_order()
+    r = ctx.spatial_order()
+    assert sorted(h.tolist()) == list(range(n))
+    w = 1.0 / np.array(ctx.stats()["grid_dim"], float).min()       # bin width
+    jh = np.linalg.norm(np.diff(xyz[h], axis=0), axis=1)
+    jr = np.linalg.norm(np.diff(xyz[r], axis=0), axis=1)
+    assert jh.max() <= 4.0 * np.sqrt(3.0) * w                      # consecutive bins are at most a bin apart (+ a rare empty bin)
+    assert jr.max() > 0.5                                          # the raster order jumps across the box
+    assert jh.mean() <= jr.mean()
+    # small and elongated sets still give a permutation
+    for pts in (oracles.uniform_seeds(7, 1), oracles.uniform_seeds(3000, 2) * np.array([1.0, 0.01, 0.01])):
+        ctx.set_points(pts)
+        assert sorted(ctx.hilbert_order().tolist()) == list(range(pts.shape[0]))
+    ctx.close()
