@@ -87,20 +87,26 @@ __global__ void sum_kernel(const double* __restrict__ v, uint32_t n, double* __r
 }
 
 struct Timer {
-    // device-side timing of a sequence of launches on the context's stream
+    // device-side timing of a sequence of launches on the context's stream; the events come from a
+    // pool owned by the context (created once, never destroyed between calls)
     std::vector<cudaEvent_t> ev;
     std::vector<int> kind;
-    cudaStream_t st;
-    explicit Timer(cudaStream_t s) : st(s) {}
+    Ctx* c;
+    explicit Timer(Ctx* ctx) : c(ctx) {}
     ~Timer() {
         for(cudaEvent_t e : ev) {
-            cudaEventDestroy(e);
+            c->event_pool.push_back(e);
         }
     }
     void mark(int k) {
         cudaEvent_t e;
-        cudaEventCreate(&e);
-        cudaEventRecord(e, st);
+        if(!c->event_pool.empty()) {
+            e = c->event_pool.back();
+            c->event_pool.pop_back();
+        } else {
+            cudaEventCreate(&e);
+        }
+        cudaEventRecord(e, c->stream);
         ev.push_back(e);
         kind.push_back(k);
     }
@@ -184,7 +190,7 @@ int cells_pipeline(Ctx* c, const b200vor_cell_params* params, bool collect_event
             return rc;
         }
     }
-    Timer T(c->stream);
+    Timer T(c);
     uint32_t k = std::min(p.k0, p.kmax);
     uint32_t nq = n;
     const uint32_t* qlist = nullptr;
@@ -420,7 +426,7 @@ int otm_newton(Ctx* c, const double* nu, double* w, const b200vor_otm_params* pr
 namespace {
 
 int ensure_grid(Ctx* c) {
-    Timer T(c->stream);
+    Timer T(c);
     T.mark(1);
     int rc = build_grid(c);
     if(rc) {
@@ -489,6 +495,10 @@ void b200vor_destroy(b200vor_ctx* h) {
     Ctx& c = h->c;
     cudaSetDevice(c.device);
     cudaStreamSynchronize(c.stream);
+    for(cudaEvent_t e : c.event_pool) {
+        cudaEventDestroy(e);
+    }
+    c.event_pool.clear();
     slab_release(&c);
     c.xyz.release(); c.wgt.release(); c.cellid.release(); c.rank.release();
     c.sub.release(); c.vstart.release(); c.vcount.release(); c.sbcount.release(); c.dom_dev.release(); c.wloc.release(); c.wloc_tmp.release();
@@ -696,7 +706,7 @@ int b200vor_knn(b200vor_ctx* h, uint32_t k, uint32_t* nbr, double* d2, int on_de
     if((c->grid_dirty || c->grid.periodic != c->periodic) && (rc = ensure_grid(c))) {
         return rc;   // the domain changed after set_points: the grid is rebuilt for the current one
     }
-    Timer T(c->stream);
+    Timer T(c);
     T.mark(1);
     KnnJob kj = {c->n, nullptr, nullptr, k, dn, dd, nullptr, 1};
     if((rc = run_knn(c, kj))) {

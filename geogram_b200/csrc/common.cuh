@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <vector>
 
 #include "../../include/b200vor.h"
 #include "grid_types.h"
@@ -71,6 +72,7 @@ struct Ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[8] = {};
+    std::vector<cudaEvent_t> event_pool;   // timing events, re-used from call to call (capi.cu: Timer)
 
     int periodic = 0;
     double period = 1.0;
