@@ -26,7 +26,7 @@ FCAP = 64
 # every symbol include/b200vor.h declares
 EXPORTS = [
     "b200vor_version", "b200vor_last_error", "b200vor_create", "b200vor_destroy",
-    "b200vor_set_domain_box", "b200vor_set_domain_periodic", "b200vor_set_domain_planes", "b200vor_set_points",
+    "b200vor_set_domain_box", "b200vor_set_domain_periodic", "b200vor_set_domain_planes", "b200vor_set_domain_pieces", "b200vor_set_domain_tets", "b200vor_set_points",
     "b200vor_knn", "b200vor_knn_points", "b200vor_compute_cells", "b200vor_get_cells",
     "b200vor_get_faces", "b200vor_get_vertices", "b200vor_get_cvt", "b200vor_otm_newton", "b200vor_get_spatial_order", "b200vor_get_hilbert_order", "b200vor_lloyd", "b200vor_get_stats",
     "b200vor_set_points_per_cell", "b200vor_set_stream", "b200vor_set_query_range",
@@ -126,6 +126,8 @@ def load_library():
     lib.b200vor_set_domain_box.argtypes = [vp, vp]
     lib.b200vor_set_domain_periodic.argtypes = [vp, dbl]
     lib.b200vor_set_domain_planes.argtypes = [vp, u32, vp]
+    lib.b200vor_set_domain_pieces.argtypes = [vp, u32, vp, vp]
+    lib.b200vor_set_domain_tets.argtypes = [vp, u32, vp, u32, vp]
     lib.b200vor_set_points.argtypes = [vp, u32, vp, u32, vp, i32]
     lib.b200vor_knn.argtypes = [vp, u32, vp, vp, i32]
     lib.b200vor_knn_points.argtypes = [vp, u32, vp, u32, vp, vp, i32]
@@ -201,6 +203,15 @@ class Context(object):
         (k <= 32; None or empty removes them); box domains only"""
         pl = np.zeros((0, 4)) if planes is None else np.ascontiguousarray(planes, np.float64).reshape(-1, 4)
         self._check(self.lib.b200vor_set_domain_planes(self.h, pl.shape[0], _ptr(pl) if pl.shape[0] else None))
+
+    def set_domain_tets(self, vertices, tets):
+        """domain = a tetrahedral mesh: vertices (nv,3) float64, tets (nt,4) indices; None removes it"""
+        if vertices is None:
+            self._check(self.lib.b200vor_set_domain_pieces(self.h, 0, None, None))
+            return
+        v = np.ascontiguousarray(vertices, np.float64)
+        t = np.ascontiguousarray(tets, np.uint32)
+        self._check(self.lib.b200vor_set_domain_tets(self.h, v.shape[0], _ptr(v), t.shape[0], _ptr(t)))
 
     def set_domain_periodic(self, period=1.0):
         self._check(self.lib.b200vor_set_domain_periodic(self.h, float(period)))

@@ -136,7 +136,7 @@ int copy_out(void* dst, const void* src, size_t bytes, int on_device, cudaStream
     return B200VOR_OK;
 }
 
-int cells_pipeline(Ctx* c, const b200vor_cell_params* params, bool collect_events) {
+int cells_pipeline_one(Ctx* c, const b200vor_cell_params* params, bool collect_events) {
     b200vor_cell_params p = {48, 384, 0, 0, 0};
     if(params) {
         p = *params;
@@ -412,6 +412,97 @@ int cells_pipeline(Ctx* c, const b200vor_cell_params* params, bool collect_event
     return B200VOR_OK;
 }
 
+// acc += the cells of one piece; status: flags of any piece, EMPTY only if empty in every piece
+__global__ void piece_accumulate_kernel(uint32_t n, int first, int want_e, const double* __restrict__ m,
+                                        const double* __restrict__ mg, const double* __restrict__ e,
+                                        const uint8_t* __restrict__ st, double* __restrict__ am,
+                                        double* __restrict__ amg, double* __restrict__ ae, uint8_t* __restrict__ ast) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) {
+        return;
+    }
+    const uint8_t s = st[i];
+    const uint8_t keep = uint8_t(s & ~uint8_t(B200VOR_CELL_EMPTY));
+    if(first) {
+        am[i] = m[i];
+        amg[3 * size_t(i)] = mg[3 * size_t(i)];
+        amg[3 * size_t(i) + 1] = mg[3 * size_t(i) + 1];
+        amg[3 * size_t(i) + 2] = mg[3 * size_t(i) + 2];
+        if(want_e) {
+            ae[i] = e[i];
+        }
+        ast[i] = s;
+    } else {
+        am[i] += m[i];
+        amg[3 * size_t(i)] += mg[3 * size_t(i)];
+        amg[3 * size_t(i) + 1] += mg[3 * size_t(i) + 1];
+        amg[3 * size_t(i) + 2] += mg[3 * size_t(i) + 2];
+        if(want_e) {
+            ae[i] += e[i];
+        }
+        const uint8_t a = ast[i];
+        ast[i] = uint8_t((a & ~uint8_t(B200VOR_CELL_EMPTY)) | keep | (a & s & uint8_t(B200VOR_CELL_EMPTY)));
+    }
+}
+
+// The cell pass.  A domain made of several convex pieces (b200vor_set_domain_pieces / _tets: the
+// tetrahedra of a mesh, generic_RVD.h:1464-1597): every cell is integrated over each piece in turn
+// (piece planes = the first candidates of the cell, fused_clip.inc) and the integrals are added up.
+int cells_pipeline(Ctx* c, const b200vor_cell_params* params, bool collect_events) {
+    const size_t np = c->piece_off.empty() ? 0 : c->piece_off.size() - 1;
+    if(np == 0) {
+        return cells_pipeline_one(c, params, collect_events);
+    }
+    b200vor_cell_params p = {0, 0, 0, 0, 0};
+    if(params) {
+        p = *params;
+    }
+    if(p.want_faces) {
+        set_error("b200vor_compute_cells: no face lists on a domain made of several pieces");
+        return B200VOR_ERR_ARG;
+    }
+    const uint32_t n = c->n;
+    int rc;
+    if((rc = c->acc_m.reserve(n)) || (rc = c->acc_mg.reserve(3 * size_t(n))) || (rc = c->acc_st.reserve(n)) ||
+       (p.want_energy && (rc = c->acc_e.reserve(n)))) {
+        return rc;
+    }
+    float ms_clip = 0.f, ms_knn = 0.f;
+    for(size_t k = 0; k < np; ++k) {
+        const uint32_t a = c->piece_off[k], b = c->piece_off[k + 1];
+        if((rc = c->dom_dev.reserve(4 * size_t(b - a)))) {
+            return rc;
+        }
+        B200_CUDA_CHECK(cudaMemcpyAsync(c->dom_dev.p, &c->piece_planes[4 * size_t(a)], 4 * size_t(b - a) * sizeof(double),
+                                        cudaMemcpyHostToDevice, c->stream));
+        c->ndom = int(b - a);
+        c->stats.ms_clip = c->stats.ms_knn = 0.f;
+        rc = cells_pipeline_one(c, &p, collect_events && k + 1 == np);
+        if(rc) {
+            c->ndom = 0;
+            return rc;
+        }
+        ms_clip += c->stats.ms_clip;
+        ms_knn += c->stats.ms_knn;
+        piece_accumulate_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(
+            n, k == 0 ? 1 : 0, p.want_energy ? 1 : 0, c->m.p, c->mg.p, p.want_energy ? c->energy.p : nullptr, c->status.p,
+            c->acc_m.p, c->acc_mg.p, p.want_energy ? c->acc_e.p : nullptr, c->acc_st.p);
+        c->stats.gpu_launches++;
+        B200_CUDA_CHECK(cudaGetLastError());
+    }
+    c->ndom = 0;
+    B200_CUDA_CHECK(cudaMemcpyAsync(c->m.p, c->acc_m.p, size_t(n) * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    B200_CUDA_CHECK(cudaMemcpyAsync(c->mg.p, c->acc_mg.p, 3 * size_t(n) * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    B200_CUDA_CHECK(cudaMemcpyAsync(c->status.p, c->acc_st.p, size_t(n), cudaMemcpyDeviceToDevice, c->stream));
+    if(p.want_energy) {
+        B200_CUDA_CHECK(cudaMemcpyAsync(c->energy.p, c->acc_e.p, size_t(n) * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    }
+    B200_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    c->stats.ms_clip = ms_clip;
+    c->stats.ms_knn = ms_knn;
+    return B200VOR_OK;
+}
+
 }  // namespace
 
 // cell pass with face lists on the context's current weights (otm.cu)
@@ -501,7 +592,7 @@ void b200vor_destroy(b200vor_ctx* h) {
     c.event_pool.clear();
     slab_release(&c);
     c.xyz.release(); c.wgt.release(); c.cellid.release(); c.rank.release();
-    c.sub.release(); c.vstart.release(); c.vcount.release(); c.sbcount.release(); c.dom_dev.release(); c.wloc.release(); c.wloc_tmp.release();
+    c.sub.release(); c.vstart.release(); c.vcount.release(); c.sbcount.release(); c.dom_dev.release(); c.acc_m.release(); c.acc_mg.release(); c.acc_e.release(); c.acc_st.release(); c.wloc.release(); c.wloc_tmp.release();
     c.cell_start.release(); c.perm.release(); c.scan_tmp.release(); c.sorted.release();
     c.knn.release(); c.knn_flag.release(); c.qlist.release(); c.qlist2.release(); c.qlist3.release(); c.qrows.release();
     c.counter.release(); c.m.release(); c.mg.release(); c.status.release();
@@ -558,7 +649,102 @@ int b200vor_set_domain_planes(b200vor_ctx* h, uint32_t n, const double* planes) 
         B200_CUDA_CHECK(cudaStreamSynchronize(c->stream));
     }
     c->ndom = int(n);
+    c->piece_off.clear();
+    c->piece_planes.clear();
     c->cells_valid = c->faces_valid = false;
+    return B200VOR_OK;
+}
+
+int b200vor_set_domain_pieces(b200vor_ctx* h, uint32_t npieces, const uint32_t* nplanes, const double* planes) {
+    if(!h || npieces > 4096 || (npieces > 0 && (!nplanes || !planes))) {
+        set_error("b200vor_set_domain_pieces: invalid argument (at most 4096 pieces)");
+        return B200VOR_ERR_ARG;
+    }
+    Ctx* c = &h->c;
+    if(npieces > 0 && c->periodic) {
+        set_error("b200vor_set_domain_pieces: box domains only");
+        return B200VOR_ERR_ARG;
+    }
+    std::vector<uint32_t> off(1, 0u);
+    for(uint32_t k = 0; k < npieces; ++k) {
+        if(nplanes[k] == 0 || nplanes[k] > 32) {
+            set_error("b200vor_set_domain_pieces: piece %u has %u planes (1..32)", k, nplanes[k]);
+            return B200VOR_ERR_ARG;
+        }
+        off.push_back(off.back() + nplanes[k]);
+    }
+    c->ndom = 0;
+    if(npieces == 0) {
+        c->piece_off.clear();
+        c->piece_planes.clear();
+    } else {
+        c->piece_off = off;
+        c->piece_planes.assign(planes, planes + 4 * size_t(off.back()));
+    }
+    c->cells_valid = c->faces_valid = false;
+    return B200VOR_OK;
+}
+
+int b200vor_set_domain_tets(b200vor_ctx* h, uint32_t nv, const double* v, uint32_t nt, const uint32_t* tets) {
+    if(!h || !v || !tets || nt == 0 || nv < 4) {
+        set_error("b200vor_set_domain_tets: invalid argument");
+        return B200VOR_ERR_ARG;
+    }
+    std::vector<uint32_t> np(nt, 4u);
+    std::vector<double> pl(16 * size_t(nt));
+    for(uint32_t t = 0; t < nt; ++t) {
+        const uint32_t* q = tets + 4 * size_t(t);
+        for(int f = 0; f < 4; ++f) {
+            if(q[f] >= nv) {
+                set_error("b200vor_set_domain_tets: vertex index out of range in tetrahedron %u", t);
+                return B200VOR_ERR_ARG;
+            }
+        }
+        for(int f = 0; f < 4; ++f) {
+            // face opposite to vertex f, normal turned towards vertex f
+            const double* a = v + 3 * size_t(q[(f + 1) & 3]);
+            const double* b = v + 3 * size_t(q[(f + 2) & 3]);
+            const double* cc = v + 3 * size_t(q[(f + 3) & 3]);
+            const double* o = v + 3 * size_t(q[f]);
+            const double ux = b[0] - a[0], uy = b[1] - a[1], uz = b[2] - a[2];
+            const double wx = cc[0] - a[0], wy = cc[1] - a[1], wz = cc[2] - a[2];
+            double nx = uy * wz - uz * wy, ny = uz * wx - ux * wz, nz = ux * wy - uy * wx;
+            double d = -(nx * a[0] + ny * a[1] + nz * a[2]);
+            const double side = nx * o[0] + ny * o[1] + nz * o[2] + d;
+            if(side == 0.0) {
+                set_error("b200vor_set_domain_tets: tetrahedron %u is flat", t);
+                return B200VOR_ERR_ARG;
+            }
+            if(side < 0.0) {
+                nx = -nx; ny = -ny; nz = -nz; d = -d;
+            }
+            double* out = &pl[16 * size_t(t) + 4 * f];
+            out[0] = nx; out[1] = ny; out[2] = nz; out[3] = d;
+        }
+    }
+    // the clipping box only has to contain the mesh; it is set a little larger than the mesh so that
+    // no plane of a tetrahedron passes exactly through a corner or an edge of the box (exact ties)
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for(uint32_t t = 0; t < nt; ++t) {
+        for(int f = 0; f < 4; ++f) {
+            const double* q = v + 3 * size_t(tets[4 * size_t(t) + f]);
+            for(int a = 0; a < 3; ++a) {
+                lo[a] = fmin(lo[a], q[a]);
+                hi[a] = fmax(hi[a], q[a]);
+            }
+        }
+    }
+    const double ext = fmax(hi[0] - lo[0], fmax(hi[1] - lo[1], hi[2] - lo[2]));
+    int rc = b200vor_set_domain_pieces(h, nt, np.data(), pl.data());
+    if(rc) {
+        return rc;
+    }
+    const double margin[3] = {0.0371, 0.0413, 0.0457};   // (unequal: no symmetric coincidence either)
+    for(int a = 0; a < 3; ++a) {
+        h->c.box[a] = lo[a] - margin[a] * ext;
+        h->c.box[3 + a] = hi[a] + margin[a] * ext;
+    }
+    h->c.periodic = 0;
     return B200VOR_OK;
 }
 
@@ -572,8 +758,8 @@ int b200vor_set_domain_periodic(b200vor_ctx* h, double period) {
         set_error("b200vor_set_domain_periodic: n too large for 32-bit periodic ids");
         return B200VOR_ERR_ARG;
     }
-    if(h->c.ndom > 0) {
-        set_error("b200vor_set_domain_periodic: remove the domain planes first (b200vor_set_domain_planes(ctx, 0, NULL))");
+    if(h->c.ndom > 0 || !h->c.piece_off.empty()) {
+        set_error("b200vor_set_domain_periodic: remove the domain planes / pieces first (b200vor_set_domain_planes(ctx, 0, NULL))");
         return B200VOR_ERR_ARG;
     }
     slab_deactivate(&h->c);

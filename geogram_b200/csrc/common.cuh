@@ -80,6 +80,11 @@ struct Ctx {
     double ppc = 8.0;
     int fused_sweep_mode = 0;      // (pipeline -> fused.cu) large-cell instance: 0 sweep in bands x4, 1 bands x1.25, 2 no sweep
     bool fused_bail_far = false;   // (pipeline -> fused.cu) far-reaching cells go straight to the large-cell instance
+    // domain = union of convex pieces (tetrahedra of a mesh ...): planes of piece p = piece_planes[piece_off[p] .. piece_off[p+1])
+    std::vector<uint32_t> piece_off;
+    std::vector<double> piece_planes;
+    DevBuf<double> acc_m, acc_mg, acc_e;   // sums over the pieces
+    DevBuf<uint8_t> acc_st;
     int ndom = 0;              // planes of the convex domain (b200vor_set_domain_planes), clipped before any neighbour
     DevBuf<double> dom_dev;
     int open = 0;              // slab-local context: open faces of the local grid (GridDesc::open)

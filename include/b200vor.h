@@ -129,6 +129,16 @@ int b200vor_set_domain_box(b200vor_ctx* ctx, const double* box);
  * by the team kernels only (a cell beyond their capacities keeps its flag). */
 #define B200VOR_DOMAIN_ID 0xFFFFFF00u
 int b200vor_set_domain_planes(b200vor_ctx* ctx, uint32_t n, const double* planes);
+/* domain = union of convex PIECES with disjoint interiors, e.g. the tetrahedra of a domain mesh (what
+ * the reference's restricted Voronoi diagram integrates over, voronoi/generic_RVD.h:1464-1597 and
+ * RVD_callback.cpp:794-858: every cell is clipped by every tetrahedron it meets and the integrals summed).
+ * Piece p has nplanes[p] (1..32) half-spaces, stored one after the other in planes.  b200vor_compute_cells /
+ * b200vor_lloyd / b200vor_get_cvt then return, per seed, the integrals over cell ∩ domain: every cell is
+ * integrated over each piece in turn (cost: one pass per piece; a cell that does not meet the piece is
+ * clipped away after a few planes).  No face lists; status EMPTY = the cell meets no piece.
+ * b200vor_set_domain_tets builds the pieces from a tetrahedral mesh (nv vertices, nt x 4 indices). */
+int b200vor_set_domain_pieces(b200vor_ctx* ctx, uint32_t npieces, const uint32_t* nplanes, const double* planes);
+int b200vor_set_domain_tets(b200vor_ctx* ctx, uint32_t nv, const double* vertices, uint32_t nt, const uint32_t* tets);
 /* periodic cube [0,period)^3; neighbour ids become real + n*instance (periodic.h:95-99) */
 int b200vor_set_domain_periodic(b200vor_ctx* ctx, double period);
 

@@ -77,3 +77,94 @@ def test_lloyd_in_convex_domain_and_api_checks(Context, port):
     with pytest.raises(B200VorError):
         ctx.set_domain_planes(dom)
     ctx.close()
+
+
+def _kuhn_tets(i, j, k, nx):
+    """the six tetrahedra of the Kuhn subdivision of the unit-lattice cube (i, j, k), vertex ids in an
+    (nx+1)^3 lattice"""
+    import itertools
+    def vid(a, b, c):
+        return a + (nx + 1) * (b + (nx + 1) * c)
+    out = []
+    for perm in itertools.permutations(range(3)):
+        p = [i, j, k]
+        t = [vid(*p)]
+        for ax in perm:
+            p[ax] += 1
+            t.append(vid(*p))
+        out.append(t)
+    return out
+
+
+def _lattice_mesh(nx, keep):
+    g = np.arange(nx + 1) / float(nx)
+    V = np.array([[g[a], g[b], g[c]] for c in range(nx + 1) for b in range(nx + 1) for a in range(nx + 1)])
+    T = []
+    for k in range(nx):
+        for j in range(nx):
+            for i in range(nx):
+                if keep(i, j, k):
+                    T += _kuhn_tets(i, j, k, nx)
+    return V, np.array(T, np.uint32)
+
+
+def test_tet_mesh_domain_cube_equals_box_domain(Context):
+    """A cube cut into 6 x 8 tetrahedra is the cube: cells integrated over the tetrahedra and summed
+    (b200vor_set_domain_tets) must equal the cells of the plain box domain."""
+    n = 40000
+    xyz = oracles.uniform_seeds(n, 41)
+    a = Context(0)
+    a.set_points(xyz)
+    a.compute_cells()
+    m0, mg0, st0 = a.get_cells()
+    V, T = _lattice_mesh(2, lambda i, j, k: True)
+    b = Context(0)
+    b.set_domain_tets(V, T)
+    b.set_points(xyz)
+    b.compute_cells()
+    m, mg, st = b.get_cells()
+    assert (st == 0).all(), dict(zip(*np.unique(st, return_counts=True)))
+    assert np.abs(m - m0).max() <= 1e-12 and np.abs(mg - mg0).max() <= 1e-12
+    assert abs(m.sum() - 1.0) < 1e-11
+    x1 = b.lloyd(1)
+    a.set_points(xyz)
+    x0 = a.lloyd(1)
+    assert np.abs(x1 - x0).max() < 1e-10
+
+
+def test_tet_mesh_domain_nonconvex_vs_reference(Context, reference):
+    """An L-shaped (non-convex) domain meshed with tetrahedra: per seed, the integrals over cell /\\ domain
+    against the unmodified reference clipping the same cell by every tetrahedron with its own ConvexCell
+    (oracle B with the tetrahedron's planes) and summing -- what generic_RVD.h:1464-1597 computes."""
+    n = 6000
+    xyz = oracles.uniform_seeds(n, 43)
+    V, T = _lattice_mesh(2, lambda i, j, k: not (i == 1 and j == 1 and k == 1))      # the cube minus one octant
+    ctx = Context(0)
+    ctx.set_domain_tets(V, T)
+    ctx.set_points(xyz)
+    ctx.compute_cells()
+    m, mg, st = ctx.get_cells()
+    assert ((st & ~np.uint8(4)) == 0).all(), dict(zip(*np.unique(st, return_counts=True)))
+    assert abs(m.sum() - 0.875) < 1e-10
+    mr = np.zeros(n)
+    mgr = np.zeros((n, 3))
+    box = [-0.1, -0.12, -0.14, 1.1, 1.12, 1.14]
+    for t in T:
+        P = V[t]
+        planes = []
+        for f in range(4):
+            a, b, c, o = P[(f + 1) % 4], P[(f + 2) % 4], P[(f + 3) % 4], P[f]
+            nrm = np.cross(b - a, c - a)
+            d = -nrm @ a
+            if nrm @ o + d < 0:
+                nrm, d = -nrm, -d
+            planes.append([nrm[0], nrm[1], nrm[2], d])
+        A = reference.cells_knn(xyz, box=box, domain=np.array(planes))
+        mr += A.m
+        mgr += A.mg
+    assert np.abs(m - mr).max() <= 1e-9 * mr.max()
+    assert np.abs(mg - mgr).max() <= 1e-9 * mr.max()
+    # seeds inside the missing octant still own the part of their cell that reaches into the domain, or nothing
+    inside_hole = (xyz > 0.5).all(axis=1)
+    assert (m[inside_hole] < m[~inside_hole].mean()).mean() > 0.5
+    ctx.close()
