@@ -475,6 +475,14 @@ int otm_newton(Ctx* c, const double* nu_in, double* w_io, const b200vor_otm_para
         set_error("b200vor_otm_newton: copy of the weights failed");
         return fail(B200VOR_ERR_CUDA);
     }
+    if(!nu_in && c->ndom > 0 && !(P.total_mass > 0.0)) {
+        set_error("b200vor_otm_newton: on a convex domain (b200vor_set_domain_planes) give nu or total_mass (= the measure of the domain)");
+        return fail(B200VOR_ERR_ARG);
+    }
+    if(!c->piece_off.empty()) {
+        set_error("b200vor_otm_newton: not available on a domain made of several pieces (no facet areas there)");
+        return fail(B200VOR_ERR_ARG);
+    }
     // measure of the domain (uniform target = |domain| / n)
     double domain = c->periodic ? c->period * c->period * c->period
                                 : (c->box[3] - c->box[0]) * (c->box[4] - c->box[1]) * (c->box[5] - c->box[2]);

@@ -168,3 +168,35 @@ def test_tet_mesh_domain_nonconvex_vs_reference(Context, reference):
     inside_hole = (xyz > 0.5).all(axis=1)
     assert (m[inside_hole] < m[~inside_hole].mean()).mean() > 0.5
     ctx.close()
+
+
+def test_otm_in_convex_domain(Context):
+    """Semi-discrete optimal transport with a convex polytope as the source domain: the Newton solver
+    equalises the Laguerre cell volumes restricted to the polytope (faces on the domain planes are
+    boundary, like box faces); the reference runs OptimalTransportMap3d on a tetrahedral mesh of such a domain
+    (src/examples/exploragram/compute_OTM/main.cpp:251-298)."""
+    from geogram_b200 import B200VorError
+    n = 20000
+    dom = _convex_domain()
+    xyz = oracles.uniform_seeds(3 * n, 47)
+    xyz = xyz[((xyz @ dom[:, :3].T + dom[:, 3]) >= 0.01).all(axis=1)][:n]
+    n = xyz.shape[0]
+    ctx = Context(0)
+    ctx.set_domain_planes(dom)
+    ctx.set_points(xyz)
+    ctx.compute_cells()
+    m0, _, st0 = ctx.get_cells()
+    assert (st0 == 0).all()
+    vol = m0.sum()
+    with pytest.raises(B200VorError):
+        ctx.otm_newton(epsilon=1e-3)                      # the measure of the domain must be given
+    w, res = ctx.otm_newton(epsilon=1e-3, total_mass=vol)
+    assert res["converged"] == 1 and res["max_rel_error"] < 2e-3
+    assert abs(res["sum_volume"] - vol) < 1e-9
+    ctx.set_points(xyz, w)
+    ctx.compute_cells()
+    m, _, st = ctx.get_cells()
+    assert (st == 0).all()
+    assert np.abs(m - vol / n).max() <= 2e-3 * vol / n
+    assert np.std(m0) > 20 * np.std(m)
+    ctx.close()
