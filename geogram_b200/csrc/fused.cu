@@ -59,6 +59,10 @@ namespace b200vor {
 #ifndef B200VOR_FUSED_WPB_TWO
 #define B200VOR_FUSED_WPB_TWO 8   // warps per block on a two-level grid (2 and 8 measured: 915 vs 843 ms at 10 M clustered seeds)
 #endif
+#ifndef B200VOR_FUSED_CHUNK_STD
+#define B200VOR_FUSED_CHUNK_STD 0   // warp-tasks per block drawn from a block-local ticket (0 = one task per warp)
+#endif
+#define B200VOR_FUSED_CHUNK B200VOR_FUSED_CHUNK_STD
 #define B200VOR_FUSED_VARIANT fused_std
 #define B200VOR_FUSED_NT 48
 #define B200VOR_FUSED_PC 40
@@ -72,10 +76,12 @@ namespace b200vor {
 #undef B200VOR_FUSED_WPB
 #undef B200VOR_FUSED_WPB_TWO
 #undef B200VOR_FUSED_MINBLOCKS
+#undef B200VOR_FUSED_CHUNK
 
 // ---- large cells (what the standard instance flags OVERFLOW / UNCERTIFIED: transiently large
 //      cells of clustered seeds, faces with more than 16 vertices): one warp per cell ----
 #define B200VOR_FUSED_VARIANT fused_big
+#define B200VOR_FUSED_CHUNK 0
 #define B200VOR_FUSED_G 32
 #define B200VOR_FUSED_WPB 4
 #define B200VOR_FUSED_WPB_TWO 4
