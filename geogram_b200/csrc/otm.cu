@@ -430,12 +430,16 @@ int vec_max(Ctx* c, Work& W, const double* w, double* out) {
 
 int otm_newton(Ctx* c, const double* nu_in, double* w_io, const b200vor_otm_params* prm, b200vor_otm_result* res,
                int on_device) {
-    b200vor_otm_params P = {50, 1000, 1e-8, 0.01, 0.0};
+    b200vor_otm_params P = {50, 1000, 0.0, 0.01, 0.0};
+    // cg_tol = 0: INEXACT Newton -- the linear system of a step is solved to a tenth of the current
+    // relative volume error (never looser than 1e-2, never tighter than epsilon / 100): the early steps,
+    // far from the solution, do not pay for 8 digits they cannot use (Eisenstat & Walker 1996)
+    bool adaptive_tol = true;
     if(prm) {
         P = *prm;
         if(P.max_newton == 0) P.max_newton = 50;
         if(P.max_cg == 0) P.max_cg = 1000;
-        if(!(P.cg_tol > 0.0)) P.cg_tol = 1e-8;
+        adaptive_tol = !(P.cg_tol > 0.0);
         if(!(P.epsilon > 0.0)) P.epsilon = 0.01;
         if(!(P.total_mass > 0.0)) P.total_mass = 0.0;
     }
@@ -545,7 +549,8 @@ int otm_newton(Ctx* c, const double* nu_in, double* w_io, const b200vor_otm_para
             return fail(rc);
         }
         // device-resident scalars; the host looks at them every 16 iterations only
-        double hsc[kNScalars] = {rz, 0.0, 0.0, bb, P.cg_tol * P.cg_tol * bb, 0.0, 0.0};
+        const double tol = adaptive_tol ? fmin(1e-2, fmax(0.1 * fmin(cur.maxrel, 1.0), 0.01 * P.epsilon)) : P.cg_tol;
+        double hsc[kNScalars] = {rz, 0.0, 0.0, bb, tol * tol * bb, 0.0, 0.0};
         double* sc = W.part.p + 4 * kNB;
         B200_CUDA_CHECK(cudaMemcpyAsync(sc, hsc, sizeof(hsc), cudaMemcpyHostToDevice, st));
         uint32_t k = 0;

@@ -193,7 +193,8 @@ int b200vor_get_cvt(b200vor_ctx* ctx, double* f_cell, double* g, double* f_total
 typedef struct b200vor_otm_params {
     uint32_t max_newton;  /* 0 = 50                                                        */
     uint32_t max_cg;      /* CG iterations per Newton step, 0 = 1000                       */
-    double cg_tol;        /* relative residual of the linear solve, 0 = 1e-8               */
+    double cg_tol;        /* relative residual of the linear solve; 0 = inexact Newton: a tenth of
+                             the current relative volume error, within [epsilon / 100, 1e-2]  */
     double epsilon;       /* stop when max_i |vol_i - nu_i| <= epsilon * nu_i, 0 = 0.01
                              (OptimalTransportMap::set_epsilon)                            */
     double total_mass;    /* nu == NULL: nu_i = total_mass / n, 0 = measure of the domain  */
