@@ -501,6 +501,16 @@ void CentroidalVoronoiTesselation::set_periodic(double period) {
     check(b200vor_set_domain_periodic(ctx_, period), "CentroidalVoronoiTesselation::set_periodic");
 }
 
+void CentroidalVoronoiTesselation::set_volumetric_mesh(index_t nb_vertices, const double* vertices, index_t nb_tets,
+                                                       const index_t* tets) {
+    check(b200vor_set_domain_tets(ctx_, nb_vertices, vertices, nb_tets, tets),
+          "CentroidalVoronoiTesselation::set_volumetric_mesh");
+}
+
+void CentroidalVoronoiTesselation::set_domain_planes(index_t nb_planes, const double* planes) {
+    check(b200vor_set_domain_planes(ctx_, nb_planes, planes), "CentroidalVoronoiTesselation::set_domain_planes");
+}
+
 void CentroidalVoronoiTesselation::set_points(index_t nb_points, const double* points) {
     points_.assign(points, points + 3 * size_t(nb_points));
     point_is_locked_.clear();

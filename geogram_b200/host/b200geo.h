@@ -189,6 +189,11 @@ public:
     ~CentroidalVoronoiTesselation();
     void set_domain_box(const double* box6);
     void set_periodic(double period);
+    /* volumetric CVT of a tetrahedral mesh, the reference's set_volumetric(true) on a mesh with cells
+       (voronoi/CVT.h, RVD.h:284-290 compute_centroids on the tetrahedra): nb_tets x 4 vertex indices */
+    void set_volumetric_mesh(index_t nb_vertices, const double* vertices, index_t nb_tets, const index_t* tets);
+    /* ... or of a convex polytope: nb_planes half-spaces a x + b y + c z + d >= 0 cutting the box */
+    void set_domain_planes(index_t nb_planes, const double* planes);
     void set_points(index_t nb_points, const double* points);
     void resize_points(index_t nb_points) { points_.resize(3 * size_t(nb_points)); }
     index_t nb_points() const { return index_t(points_.size() / 3); }

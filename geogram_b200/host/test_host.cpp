@@ -157,6 +157,26 @@ int main() {
         v1 += (c2.volume(c) - 1.0 / n) * (c2.volume(c) - 1.0 / n);
     }
     EXPECT(v1 < 0.6 * v0);
+    // ---- volumetric CVT of a tetrahedral mesh (one cube cut into six tetrahedra = the cube): the same
+    //      Lloyd iterate as on the box domain
+    {
+        const double V[8][3] = {{0, 0, 0}, {1, 0, 0}, {0, 1, 0}, {1, 1, 0}, {0, 0, 1}, {1, 0, 1}, {0, 1, 1}, {1, 1, 1}};
+        const index_t T[6][4] = {{0, 1, 3, 7}, {0, 1, 5, 7}, {0, 2, 3, 7}, {0, 2, 6, 7}, {0, 4, 5, 7}, {0, 4, 6, 7}};
+        CentroidalVoronoiTesselation a(3), b(3);
+        a.set_points(n, pts.data());
+        a.Lloyd_iterations(1);
+        b.set_volumetric_mesh(8, &V[0][0], 6, &T[0][0]);
+        b.set_points(n, pts.data());
+        b.Lloyd_iterations(1);
+        double dmax = 0.0;
+        for(index_t i = 0; i < n; ++i) {
+            for(int k = 0; k < 3; ++k) {
+                dmax = std::max(dmax, fabs(a.embedding(i)[k] - b.embedding(i)[k]));
+            }
+        }
+        printf("Lloyd on the cube as 6 tetrahedra vs box domain: max difference %.2e\n", dmax);
+        EXPECT(dmax < 1e-10);
+    }
     // ---- funcgrad (CVT.cpp:323-341): f decreases under Lloyd, g = 0 on the locked point, and
     //      a finite difference of f along -g matches |g|^2 (the CVT gradient formula)
     {
