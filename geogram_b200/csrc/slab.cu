@@ -637,7 +637,7 @@ int build_local(Ctx* c) {
     B200_CUDA_CHECK(cudaStreamSynchronize(st));
     const uint32_t nsend = off[W];
     SLAB_TRACE(c, "x-pack: %u to send, H %.4f", nsend, S->H);
-    if((rc = S->sendbuf.reserve(size_t(nsend) * kGhostDoubles + 8))) {
+    if((rc = S->sendbuf.reserve((size_t(nsend) + nsend / 4) * kGhostDoubles + 8))) {   // (ghost counts grow as the seeds relax)
         return rc;
     }
     XEmit xe;
@@ -673,7 +673,7 @@ int build_local(Ctx* c) {
         roff[p + 1] = roff[p] + mat[size_t(p) * W + S->rank];   // what peer p sends to me
     }
     const uint32_t nrecv = roff[W];
-    if((rc = S->recvbuf.reserve(size_t(nrecv) * kGhostDoubles + 8))) {
+    if((rc = S->recvbuf.reserve((size_t(nrecv) + nrecv / 4) * kGhostDoubles + 8))) {
         return rc;
     }
     cudaEventRecord(S->ev[1], st);
