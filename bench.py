@@ -457,7 +457,7 @@ def main():
     #      this rank's updated rows back (D2H).  Iterations K+1.. of the same run. ----
     e2e_value, e2e_steps = None, 0
     if not args.no_e2e:
-        e2e_steps = min(args.steps, 5)
+        e2e_steps = args.steps          # the same iterations 1..K as the device-timed `value`
         host_in = torch.empty((hi - lo, 3), dtype=torch.float64).pin_memory()
         host_out = torch.empty((hi - lo, 3), dtype=torch.float64).pin_memory()
         # start again from the raw seeds: this rank's rows of the (slab-ordered) raw array
