@@ -103,6 +103,28 @@ def test_slab_requeues_with_a_wider_halo(Context):
     assert np.abs(m - m0).max() <= 1e-12 * m0.max()
 
 
+@pytest.mark.parametrize("periodic", [False, True])
+def test_slab_clustered_seeds_flag_never_wrong(Context, periodic):
+    """Clustered seeds on the slab path (two-level local grid, sweep of far-reaching cells): a cell whose
+    security ball leaves the local grid is re-queued with a wider halo and, if it still does at the widest
+    one, comes back UNCERTIFIED -- every other cell equals the single-context cell."""
+    n = 60000
+    xyz = oracles.clustered_seeds(n, 4321)
+    m0, _, st0, _, _, _ = _single(Context, xyz, periodic, faces=False)
+    ctx = Context(0)
+    if periodic:
+        ctx.set_domain_periodic(1.0)
+    ctx.slab_set_points(xyz, 0, n)
+    ctx.slab_compute_cells()
+    m, _, st = ctx.get_cells()
+    assert ((st & ~np.uint8(1 | 8)) == 0).all(), np.bincount(st)
+    ok = (st == 0) & (st0 == 0)
+    assert ok.sum() >= n - 30
+    assert (np.abs(m - m0)[ok] <= 1e-12 * m0[ok]).all()
+    if not periodic:
+        assert (st == 0).all() and ctx.slab_stats()["retries"] == 0
+
+
 def test_slab_two_ranks_vs_single_context():
     import torch
     if torch.cuda.device_count() < 2:
