@@ -46,6 +46,10 @@
 
 namespace b200vor {
 
+#ifndef B200VOR_FUSED_F32
+#define B200VOR_FUSED_F32 0   // fp32 filter of the sign tests (A/B: DESIGN.md section 9)
+#endif
+
 // ---- standard cells: 16 lanes per cell, two cells per warp ----
 #ifndef B200VOR_FUSED_MINBLOCKS
 #define B200VOR_FUSED_MINBLOCKS 2
