@@ -46,6 +46,9 @@
 
 namespace b200vor {
 
+#ifndef B200VOR_FAR_RING
+#define B200VOR_FAR_RING 4   // two-level walk: fine rings offered before a cell counts as far-reaching (sweep)
+#endif
 #ifndef B200VOR_FUSED_F32
 #define B200VOR_FUSED_F32 0   // fp32 filter of the sign tests (A/B: DESIGN.md section 9)
 #endif
