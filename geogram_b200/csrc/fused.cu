@@ -46,6 +46,9 @@
 
 namespace b200vor {
 
+#ifndef B200VOR_FILT_AFTER
+#define B200VOR_FILT_AFTER 1   // two-level walk: halvings of an overflowing shell before the filtered scan (0 / 1 / 2 / 4 measured: 614 / 560 / 575 / 684 ms at 10 M clustered seeds)
+#endif
 #ifndef B200VOR_PYR_MIN_BINS
 #define B200VOR_PYR_MIN_BINS 512   // two-level walk: boxes of more level-1 bins than this are walked super-bin by super-bin (0 / 64 / 512 measured: 701 / 644 / 639 ms at 10 M clustered seeds)
 #endif
