@@ -863,6 +863,10 @@ int b200vor_set_points(b200vor_ctx* h, uint32_t n, const double* xyz, uint32_t s
 }
 
 int b200vor_knn(b200vor_ctx* h, uint32_t k, uint32_t* nbr, double* d2, int on_device) {
+    if(h && slab_active(&h->c)) {
+        set_error("b200vor_knn: not available on a slab context (b200vor_slab_set_points)");
+        return B200VOR_ERR_ARG;
+    }
     if(!h || !nbr || k == 0) {
         set_error("b200vor_knn: invalid argument");
         return B200VOR_ERR_ARG;
@@ -959,6 +963,10 @@ int b200vor_knn_points(b200vor_ctx* h, uint32_t nq, const double* q, uint32_t k,
 }
 
 int b200vor_compute_cells(b200vor_ctx* h, const b200vor_cell_params* params) {
+    if(h && slab_active(&h->c)) {
+        set_error("b200vor_compute_cells: the context holds a slab (b200vor_slab_set_points): use the b200vor_slab_* calls");
+        return B200VOR_ERR_ARG;
+    }
     if(!h) {
         set_error("b200vor_compute_cells: null context");
         return B200VOR_ERR_ARG;
@@ -1073,6 +1081,10 @@ int b200vor_get_vertices(b200vor_ctx* h, uint32_t* nverts, double* vert_xyz, uin
 
 int b200vor_otm_newton(b200vor_ctx* h, const double* nu, double* w, const b200vor_otm_params* params,
                        b200vor_otm_result* result, int on_device) {
+    if(h && slab_active(&h->c)) {
+        set_error("b200vor_otm_newton: not available on a slab context (b200vor_slab_set_points)");
+        return B200VOR_ERR_ARG;
+    }
     if(!h || !w || h->c.n == 0) {
         set_error("b200vor_otm_newton: needs a context with points and a weight array");
         return B200VOR_ERR_ARG;
@@ -1114,6 +1126,10 @@ int b200vor_get_faces(b200vor_ctx* h, uint32_t* nfaces, uint32_t* face_nbr, doub
 
 int b200vor_lloyd(b200vor_ctx* h, uint32_t iters, const b200vor_cell_params* params,
                   double* xyz_out, int on_device) {
+    if(h && slab_active(&h->c)) {
+        set_error("b200vor_lloyd: the context holds a slab (b200vor_slab_set_points): use the b200vor_slab_* calls");
+        return B200VOR_ERR_ARG;
+    }
     if(!h || h->c.n == 0) {
         set_error("b200vor_lloyd: no points");
         return B200VOR_ERR_ARG;

@@ -187,6 +187,7 @@ int ctx_cells(Ctx* c, const b200vor_cell_params* params, bool collect_events);
 // slab.cu
 void slab_release(Ctx* c);
 uint32_t out_rows(const Ctx* c);   // rows the result getters return: n, or the own rows of a slab
+bool slab_active(const Ctx* c);     // b200vor_slab_set_points was the last set_points
 void slab_deactivate(Ctx* c);      // back to a plain single-GPU context (b200vor_set_points)
 // microbench.cu
 int microbench(Ctx* c, b200vor_peaks* out);

@@ -930,6 +930,10 @@ void reset_step_stats(Slab* S) {
 
 }  // namespace
 
+bool slab_active(const Ctx* c) {
+    return c->slab && c->slab->active;
+}
+
 uint32_t out_rows(const Ctx* c) {
     return (c->slab && c->slab->active) ? c->slab->n_own : c->n;
 }

@@ -83,6 +83,14 @@ def test_slab_world1_lloyd_equals_single_context(Context):
     assert np.abs(xa - xb).max() < 1e-12
     s = b.slab_stats()
     assert s["retries"] == 0 and s["n_flagged"] == 0
+    # a slab context refuses the single-context calls (its point array holds ghosts) until set_points
+    from geogram_b200 import B200VorError
+    for call in (lambda: b.compute_cells(), lambda: b.lloyd(1), lambda: b.knn(4)):
+        with pytest.raises(B200VorError):
+            call()
+    b.set_points(xyz)
+    b.compute_cells()
+    assert (b.get_cells()[2] == 0).all()
 
 
 def test_slab_requeues_with_a_wider_halo(Context):
