@@ -9,8 +9,9 @@ volume/centroid integration -> seed update.  Workload at N=1: BASELINE configs[1
 warm-up iterations run on a scratch copy, then the RAW uniform seeds are loaded again and the
 timed steps are Lloyd iterations 1..K from them (`ms_iter` lists every iteration, so the
 dear first iteration and the relaxed steady state are both visible).  At N>1: the
-weak-scaling shape of configs[4] (12.5 M seeds per GPU, cells sharded by x-slab, updated
-seeds all-gathered over NCCL each iteration).  At N=1 the line also carries short
+weak-scaling shape of configs[4] (12.5 M seeds per GPU; every rank keeps one x-slab plus a halo of
+ghost seeds exchanged with ncclSend/Recv inside the library, `--sharding replicated` = the
+round-1 all-gather of all seeds).  At N=1 the line also carries short
 sub-results for configs[2] (Laguerre pass + OT solve), configs[3] (clustered seeds) and the
 12.5 M-seed point of the weak-scaling curve under `extra_configs`.
 
@@ -569,7 +570,8 @@ def main():
         ctx.lloyd_device(0, xyz_relaxed.data_ptr())
         extra = extra_configs(torch, dev, ctx, xyz_relaxed, n_cells, args)
         del xyz_relaxed
-        # 12.5 M-seed point of the weak-scaling curve (configs[4] at N=1): 3 iterations from raw seeds
+        # 12.5 M-seed point of the weak-scaling curve (configs[4] at N=1): the SAME iterations 1..K from raw
+        # seeds as an N>1 run times per GPU, so that value(N) / (N * this rate) is the weak-scaling efficiency
         n_w = 12500000
         if n_cells != n_w:
             full_w = raw_seeds(n_w)
@@ -578,15 +580,18 @@ def main():
             job_w.step()
             job_w.set_seeds_device(full_w)
             torch.cuda.synchronize()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(stream)
-            for _ in range(3):
+            ev_w = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+            ev_w[0].record(stream)
+            for k in range(args.steps):
                 job_w.step()
-            b.record(stream)
+                ev_w[k + 1].record(stream)
             torch.cuda.synchronize()
-            extra["configs4_weak_n1"] = {"workload": "12.5 M uniform periodic seeds on 1 GPU, Lloyd iterations 1..3 from raw seeds",
-                                         "seeds": n_w, "ms_per_step": a.elapsed_time(b) / 3,
-                                         "cells_per_s": n_w * 3 / (a.elapsed_time(b) * 1e-3)}
+            ms_w = ev_w[0].elapsed_time(ev_w[-1])
+            extra["configs4_weak_n1"] = {"workload": "12.5 M uniform periodic seeds on 1 GPU, Lloyd iterations 1..%d from raw "
+                                                     "seeds (the per-GPU load of the N>1 runs)" % args.steps,
+                                         "seeds": n_w, "ms_per_step": ms_w / args.steps,
+                                         "ms_iter": [ev_w[k].elapsed_time(ev_w[k + 1]) for k in range(args.steps)],
+                                         "cells_per_s": n_w * args.steps / (ms_w * 1e-3)}
             del full_w, job_w
 
     line = {
