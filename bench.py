@@ -56,23 +56,70 @@ class ClockSampler(threading.Thread):
         threading.Thread.__init__(self)
         self.daemon = True
         self.index = index
-        self.samples = []
+        self.samples = []       # (perf_counter, fields)
+        self.t_begin = None
+        self.proc = None
         self.stop_flag = False
+        self.first = threading.Event()
+
+    def start(self):
+        """ONE nvidia-smi process for the whole run (the recipe's `-lms` loop), started and past its
+        initialisation BEFORE the timed region: a fresh nvidia-smi per sample initialises NVML on every
+        GPU of the box each time, which can hold up the CUDA calls of the ranks for milliseconds."""
+        import shutil
+        cmd = ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+               "--format=csv,noheader,nounits", "-lms", "100"]
+        if shutil.which("stdbuf"):
+            cmd = ["stdbuf", "-oL"] + cmd      # line-buffered although stdout is a pipe
+        try:
+            self.proc = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+        threading.Thread.start(self)
+        if self.proc is not None:
+            t0 = time.perf_counter()
+            while not self.first.wait(timeout=0.1):
+                if self.proc.poll() is not None or time.perf_counter() - t0 > 8.0:
+                    # no line came through (missing tool, buffered pipe): one nvidia-smi call per sample instead
+                    self.proc.kill()
+                    break
+
+    def begin(self):
+        """the timed region starts now: only samples taken from here on count"""
+        self.t_begin = time.perf_counter()
 
     def run(self):
+        if self.proc is not None:
+            for line in self.proc.stdout:
+                f = [x.strip() for x in line.strip().split(",")]
+                if len(f) >= 7:
+                    self.samples.append((time.perf_counter(), f))
+                    self.first.set()
+            if self.first.is_set():
+                return
         while not self.stop_flag:
             try:
                 out = subprocess.check_output(
                     ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                      "--format=csv,noheader,nounits"], timeout=5).decode().strip()
-                self.samples.append([x.strip() for x in out.split(",")])
+                self.samples.append((time.perf_counter(), [x.strip() for x in out.split(",")]))
             except Exception:
                 pass
             time.sleep(0.1)
 
     def summary(self):
+        t_end = time.perf_counter()
         self.stop_flag = True
+        if self.proc is not None and self.proc.poll() is None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
         self.join(timeout=6)
+        t0 = self.t_begin if self.t_begin is not None else 0.0
+        inside = [f for (t, f) in self.samples if t0 <= t <= t_end]
+        self.samples = inside
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         sm = sorted(float(s[0]) for s in self.samples)
@@ -430,6 +477,8 @@ def main():
     if sampler:
         sampler.start()
     barrier()
+    if sampler:
+        sampler.begin()
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     clip_iter = []
     evs[0].record(stream)

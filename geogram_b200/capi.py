@@ -92,7 +92,8 @@ class SlabStats(ctypes.Structure):
                 ("n_local", ctypes.c_uint32), ("retries", ctypes.c_uint32), ("n_flagged", ctypes.c_uint32),
                 ("halo", ctypes.c_double), ("slab_lo", ctypes.c_double), ("slab_hi", ctypes.c_double),
                 ("ms_exchange", ctypes.c_float), ("ms_pack", ctypes.c_float), ("ms_grid", ctypes.c_float),
-                ("ms_clip", ctypes.c_float), ("bytes_sent", ctypes.c_uint64), ("bytes_received", ctypes.c_uint64)]
+                ("ms_clip", ctypes.c_float), ("bytes_sent", ctypes.c_uint64), ("bytes_received", ctypes.c_uint64),
+                ("reallocs", ctypes.c_uint64)]
 
 
 class Peaks(ctypes.Structure):

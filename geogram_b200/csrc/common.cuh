@@ -42,6 +42,13 @@ __device__ inline Seed load_seed(const Seed* p) {
 // ---------------------------------------------------------------------------------
 // Context
 // ---------------------------------------------------------------------------------
+// device (re-)allocations of this process so far: a cudaFree + cudaMalloc in the middle of a run stalls
+// the stream for milliseconds, so the slab statistics report how many a call made
+inline uint64_t& devbuf_alloc_count() {
+    static uint64_t count = 0;
+    return count;
+}
+
 template <class T> struct DevBuf {
     T* p = nullptr;
     size_t cap = 0;   // elements
@@ -57,7 +64,13 @@ template <class T> struct DevBuf {
         size_t want = n + n / 8 + 64;   // (slack: sizes that drift upwards from call to call do not re-allocate each time)
         B200_CUDA_CHECK(cudaMalloc(&p, want * sizeof(T)));
         cap = want;
+        devbuf_alloc_count()++;
         return B200VOR_OK;
+    }
+    // for sizes that keep drifting upwards (ghost counts of a relaxing seed set): nothing happens while
+    // `need` fits; a buffer that has to grow is allocated with half as much again
+    int reserve_growing(size_t need) {
+        return need <= cap ? B200VOR_OK : reserve(need + need / 2);
     }
     void release() {
         if(p) {

@@ -126,6 +126,7 @@ struct Slab {
     double center = 0.0;                   // periodic domain: the own seeds are taken at their image next to it
     bool bounds_valid = false;             // lo / hi describe the current own seeds
     b200vor_slab_stats st = {};
+    uint64_t alloc0 = 0;   // devbuf_alloc_count() when the current call began
     cudaEvent_t ev[4] = {};
 };
 
@@ -637,7 +638,7 @@ int build_local(Ctx* c) {
     B200_CUDA_CHECK(cudaStreamSynchronize(st));
     const uint32_t nsend = off[W];
     SLAB_TRACE(c, "x-pack: %u to send, H %.4f", nsend, S->H);
-    if((rc = S->sendbuf.reserve((size_t(nsend) + nsend / 4) * kGhostDoubles + 8))) {   // (ghost counts grow as the seeds relax)
+    if((rc = S->sendbuf.reserve_growing(size_t(nsend) * kGhostDoubles + 8))) {   // (ghost counts grow as the seeds relax)
         return rc;
     }
     XEmit xe;
@@ -673,7 +674,7 @@ int build_local(Ctx* c) {
         roff[p + 1] = roff[p] + mat[size_t(p) * W + S->rank];   // what peer p sends to me
     }
     const uint32_t nrecv = roff[W];
-    if((rc = S->recvbuf.reserve((size_t(nrecv) + nrecv / 4) * kGhostDoubles + 8))) {
+    if((rc = S->recvbuf.reserve_growing(size_t(nrecv) * kGhostDoubles + 8))) {
         return rc;
     }
     cudaEventRecord(S->ev[1], st);
@@ -714,8 +715,10 @@ int build_local(Ctx* c) {
     // room for the y / z images as well (as many as last time + 15 %: the ghost counts drift by a per
     // cent per Lloyd step, and growing a GB-sized buffer in the middle of a run costs 100+ ms)
     const size_t want = size_t(nx) + size_t(S->st.n_ghost_yz) + (size_t(nx) + S->st.n_ghost_yz) / 7 + 4096;
-    if((rc = c->xyz.reserve(3 * want)) || (rc = S->lgid.reserve(want)) || (rc = S->ltc.reserve(want)) ||
-       (S->has_w && (rc = c->wgt.reserve(want)))) {
+    if(3 * want <= c->xyz.cap && want <= S->lgid.cap && want <= S->ltc.cap && (!S->has_w || want <= c->wgt.cap)) {
+        // fits
+    } else if((rc = c->xyz.reserve(3 * (want + want / 8))) || (rc = S->lgid.reserve(want + want / 8)) ||
+              (rc = S->ltc.reserve(want + want / 8)) || (S->has_w && (rc = c->wgt.reserve(want + want / 8)))) {
         return rc;
     }
     assemble_kernel<<<(nx + 255) / 256, 256, 0, st>>>(n_own, nrecv, S->own.p, S->has_w ? S->own_w.p : nullptr,
@@ -926,6 +929,7 @@ int slab_pass(Ctx* c, const b200vor_cell_params* params, bool lloyd) {
 void reset_step_stats(Slab* S) {
     S->st.ms_exchange = S->st.ms_pack = S->st.ms_grid = S->st.ms_clip = 0.f;
     S->st.bytes_sent = S->st.bytes_received = 0;
+    S->alloc0 = devbuf_alloc_count();
 }
 
 }  // namespace
@@ -1168,6 +1172,7 @@ int b200vor_slab_get_stats(b200vor_ctx* h, b200vor_slab_stats* out) {
         return B200VOR_ERR_ARG;
     }
     *out = h->c.slab->st;
+    out->reallocs = devbuf_alloc_count() - h->c.slab->alloc0;
     return B200VOR_OK;
 }
 

@@ -661,22 +661,31 @@ void CentroidalVoronoiTesselation::Lloyd_iterations(index_t nb_iter) {
 
 // ------------------------------------------------------------------ OptimalTransportMap3d
 OptimalTransportMap3d::OptimalTransportMap3d()
-    : ctx_(new_context()), epsilon_(0.01), converged_(false), newton_iters_(0) {}
+    : ctx_(new_context()), epsilon_(0.01), converged_(false), newton_iters_(0), period_(0.0), has_box_(false) {
+    for(int i = 0; i < 6; ++i) {
+        box_[i] = (i < 3) ? 0.0 : 1.0;
+    }
+}
 
 OptimalTransportMap3d::~OptimalTransportMap3d() { b200vor_destroy(ctx_); }
 
 void OptimalTransportMap3d::set_domain_box(const double* box6) {
     check(b200vor_set_domain_box(ctx_, box6), "OptimalTransportMap3d::set_domain_box");
+    std::copy(box6, box6 + 6, box_);
+    has_box_ = true;
+    period_ = 0.0;
 }
 
 void OptimalTransportMap3d::set_periodic(double period) {
     check(b200vor_set_domain_periodic(ctx_, period), "OptimalTransportMap3d::set_periodic");
+    period_ = period;
 }
 
 void OptimalTransportMap3d::set_points(index_t nb_points, const double* points) {
     points_.assign(points, points + 3 * size_t(nb_points));
     weights_.assign(nb_points, 0.0);
     nu_.clear();
+    level_iters_.clear();
     converged_ = false;
 }
 
@@ -685,6 +694,37 @@ void OptimalTransportMap3d::set_nu(index_t i, double nu) {
         nu_.assign(weights_.size(), -1.0);
     }
     nu_[i] = nu;
+}
+
+// Newton solve on the points [0, e) at the current weights_[0, e); target masses: nu_ rescaled so
+// that the prefix carries the whole measure (uniform when nu_ is not set)
+void OptimalTransportMap3d::solve_prefix(index_t e, index_t max_iterations, const char* who) {
+    check(b200vor_set_points(ctx_, e, points_.data(), 3, nullptr, 0), who);
+    std::vector<double> nu_level;
+    if(!nu_.empty()) {
+        double all = 0.0, part = 0.0;
+        for(size_t i = 0; i < nu_.size(); ++i) {
+            all += nu_[i];
+            if(i < e) {
+                part += nu_[i];
+            }
+        }
+        nu_level.assign(nu_.begin(), nu_.begin() + e);
+        const double s = all / part;
+        if(e != nu_.size()) {
+            for(index_t i = 0; i < e; ++i) {
+                nu_level[i] *= s;
+            }
+        }
+    }
+    b200vor_otm_params p;
+    memset(&p, 0, sizeof(p));
+    p.max_newton = max_iterations;
+    p.epsilon = epsilon_;
+    b200vor_otm_result r;
+    check(b200vor_otm_newton(ctx_, nu_level.empty() ? nullptr : nu_level.data(), weights_.data(), &p, &r, 0), who);
+    converged_ = r.converged != 0;
+    newton_iters_ = r.newton_iters;
 }
 
 void OptimalTransportMap3d::optimize(index_t max_iterations) {
@@ -697,19 +737,58 @@ void OptimalTransportMap3d::optimize(index_t max_iterations) {
             throw std::runtime_error("OptimalTransportMap3d::optimize: set_nu must be called for every point or for none");
         }
     }
-    check(b200vor_set_points(ctx_, n, points_.data(), 3, nullptr, 0), "OptimalTransportMap3d::optimize (set_points)");
-    b200vor_otm_params p;
-    memset(&p, 0, sizeof(p));
-    p.max_newton = max_iterations;
-    p.epsilon = epsilon_;
-    b200vor_otm_result r;
-    check(b200vor_otm_newton(ctx_, nu_.empty() ? nullptr : nu_.data(), weights_.data(), &p, &r, 0),
-          "OptimalTransportMap3d::optimize");
-    converged_ = r.converged != 0;
-    newton_iters_ = r.newton_iters;
+    solve_prefix(n, max_iterations, "OptimalTransportMap3d::optimize");
     measure_.resize(n);
     mg_.resize(3 * size_t(n));
     check(b200vor_get_cells(ctx_, measure_.data(), mg_.data(), nullptr, 0), "OptimalTransportMap3d::optimize (get_cells)");
+}
+
+void OptimalTransportMap3d::optimize_levels(const std::vector<index_t>& levels, index_t max_iterations) {
+    const char* who = "OptimalTransportMap3d::optimize_levels";
+    const index_t n = nb_points();
+    if(n == 0) {
+        return;
+    }
+    if(levels.size() < 2 || levels.front() != 0 || levels.back() != n) {
+        throw std::runtime_error(std::string(who) + ": levels must run from 0 to nb_points");
+    }
+    for(size_t l = 0; l + 1 < levels.size(); ++l) {
+        if(levels[l + 1] <= levels[l]) {
+            throw std::runtime_error(std::string(who) + ": levels must increase");
+        }
+    }
+    for(size_t i = 0; i < nu_.size(); ++i) {
+        if(!(nu_[i] > 0.0)) {
+            throw std::runtime_error(std::string(who) + ": set_nu must be called for every point or for none");
+        }
+    }
+    level_iters_.clear();
+    std::vector<uint32_t> nearest;
+    for(size_t l = 0; l + 1 < levels.size(); ++l) {
+        const index_t b = levels[l], e = levels[l + 1];
+        if(b != 0) {
+            // the context still holds the points [0, b) of the level below: every new point takes
+            // the weight of its nearest solved point.  The by-point query is a box query: on a
+            // periodic cube it runs on the cube without the wrap (a start value, not a result).
+            if(period_ > 0.0) {
+                const double cube[6] = {0.0, 0.0, 0.0, period_, period_, period_};
+                check(b200vor_set_domain_box(ctx_, cube), who);
+            }
+            nearest.resize(e - b);
+            check(b200vor_knn_points(ctx_, e - b, points_.data() + 3 * size_t(b), 1, nearest.data(), nullptr, 0), who);
+            if(period_ > 0.0) {
+                check(b200vor_set_domain_periodic(ctx_, period_), who);
+            }
+            for(index_t i = b; i < e; ++i) {
+                weights_[i] = weights_[nearest[i - b]];
+            }
+        }
+        solve_prefix(e, max_iterations, who);
+        level_iters_.push_back(newton_iters_);
+    }
+    measure_.resize(n);
+    mg_.resize(3 * size_t(n));
+    check(b200vor_get_cells(ctx_, measure_.data(), mg_.data(), nullptr, 0), who);
 }
 
 vec3 OptimalTransportMap3d::cell_centroid(index_t i) const {

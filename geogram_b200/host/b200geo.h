@@ -243,6 +243,16 @@ public:
     void set_epsilon(double eps) { epsilon_ = eps; }
     /* damped Newton iterations on the weights, all on the device */
     void optimize(index_t max_iterations);
+    /* multilevel solve (OptimalTransportMap::optimize_levels, call site
+       src/examples/exploragram/compute_OTM/main.cpp:292-297): `levels` = {0, e_1, ..., nb_points} as
+       filled by the reference's sampling (points in BRIO order: every prefix [0, e_l) is a uniform
+       sub-sample).  Level l solves the transport problem of the points [0, e_l) alone (target
+       masses rescaled to the measure of the domain); the points that enter at the next level
+       start from the weight of their nearest solved point (one batched by-point kNN query on
+       the device), so that the finest level starts next to its solution. */
+    void optimize_levels(const std::vector<index_t>& levels, index_t max_iterations);
+    /* Newton iterations of every level of the last optimize_levels call */
+    const std::vector<index_t>& level_newton_iterations() const { return level_iters_; }
     index_t nb_points() const { return index_t(weights_.size()); }
     double weight(index_t i) const { return weights_[i]; }
     /* measure of the Laguerre cell of point i at the current weights */
@@ -257,6 +267,11 @@ private:
     double epsilon_;
     bool converged_;
     index_t newton_iters_;
+    std::vector<index_t> level_iters_;
+    double period_;        /* > 0: periodic cube */
+    double box_[6];
+    bool has_box_;
+    void solve_prefix(index_t e, index_t max_iterations, const char* who);
 };
 
 }  // namespace B200GEO

@@ -287,6 +287,54 @@ int main() {
         EXPECT(fabs(total - 1.0) < 1e-9);
         EXPECT(otm.nb_newton_iterations() > 0 && otm.nb_newton_iterations() < 30);
     }
+    // ---- optimize_levels (compute_OTM/main.cpp:292-297): a non-uniform target, three levels; same
+    //      transport map as the single-level solve, the finest level starts next to its solution
+    {
+        const double* p = cvt.embedding(0);
+        std::vector<double> nu(n);
+        double s = 0.0;
+        for(index_t i = 0; i < n; ++i) {
+            nu[i] = 1.0 + p[3 * size_t(i)];
+            s += nu[i];
+        }
+        OptimalTransportMap3d one, ml;
+        one.set_points(n, p);
+        ml.set_points(n, p);
+        for(index_t i = 0; i < n; ++i) {
+            one.set_nu(i, nu[i] / s);
+            ml.set_nu(i, nu[i] / s);
+        }
+        one.set_epsilon(1e-4);
+        ml.set_epsilon(1e-4);
+        one.optimize(50);
+        std::vector<index_t> levels;
+        levels.push_back(0);
+        levels.push_back(n / 16);
+        levels.push_back(n / 4);
+        levels.push_back(n);
+        ml.optimize_levels(levels, 50);
+        EXPECT(one.converged() && ml.converged());
+        EXPECT(ml.level_newton_iterations().size() == 3);
+        double worst = 0.0, total = 0.0, mean1 = 0.0, meanl = 0.0, dw = 0.0, range = 0.0;
+        for(index_t i = 0; i < n; ++i) {
+            worst = std::max(worst, fabs(ml.cell_measure(i) * s / nu[i] - 1.0));
+            total += ml.cell_measure(i);
+            mean1 += one.weight(i) / n;
+            meanl += ml.weight(i) / n;
+        }
+        for(index_t i = 0; i < n; ++i) {
+            dw = std::max(dw, fabs((ml.weight(i) - meanl) - (one.weight(i) - mean1)));
+            range = std::max(range, fabs(one.weight(i) - mean1));
+        }
+        EXPECT(worst <= 1e-4);
+        EXPECT(fabs(total - 1.0) < 1e-9);
+        // weights are defined up to a constant; both solves stop within epsilon of the same optimum
+        EXPECT(dw <= 1e-2 * range);
+        EXPECT(ml.level_newton_iterations().back() <= one.nb_newton_iterations());
+        printf("optimize_levels: Newton iterations per level %u %u %u (single level: %u), max weight difference %.2e of range %.2e\n",
+               unsigned(ml.level_newton_iterations()[0]), unsigned(ml.level_newton_iterations()[1]),
+               unsigned(ml.level_newton_iterations()[2]), unsigned(one.nb_newton_iterations()), dw, range);
+    }
     printf(fails ? "host test: %d FAILURES\n" : "host test: ok\n", fails);
     return fails ? 1 : 0;
 }

@@ -245,7 +245,7 @@ class SlabLloyd(object):
         self._comm_ms += s["ms_exchange"] + s["ms_pack"]
         self.retries += s["retries"]
         self.steps.append({k: (round(s[k], 3) if isinstance(s[k], float) else s[k])
-                           for k in ("ms_exchange", "ms_pack", "ms_grid", "ms_clip", "n_local", "retries")})
+                           for k in ("ms_exchange", "ms_pack", "ms_grid", "ms_clip", "n_local", "retries", "reallocs")})
 
     def get_shard_host(self, host_rows):
         self.ctx.slab_lloyd_device(0, self.mine.data_ptr())

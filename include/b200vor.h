@@ -278,6 +278,7 @@ typedef struct b200vor_slab_stats {
     double slab_lo, slab_hi;
     float ms_exchange, ms_pack, ms_grid, ms_clip;   /* device ms, summed over the passes of the last call */
     uint64_t bytes_sent, bytes_received;            /* ghost traffic of this rank over the last call      */
+    uint64_t reallocs;     /* device buffers (re-)allocated during the last call: 0 once the sizes settled */
 } b200vor_slab_stats;
 /* rank 0 creates the id (an ncclUniqueId), the caller hands the 128 bytes to every rank (MPI, torch, files) */
 int b200vor_comm_unique_id(void* id);
