@@ -4,6 +4,7 @@
 
 #include <stdio.h>
 #include <string.h>
+#include <math.h>
 
 #include <fstream>
 
@@ -722,7 +723,23 @@ void OptimalTransportMap3d::solve_prefix(index_t e, index_t max_iterations, cons
     p.max_newton = max_iterations;
     p.epsilon = epsilon_;
     b200vor_otm_result r;
-    check(b200vor_otm_newton(ctx_, nu_level.empty() ? nullptr : nu_level.data(), weights_.data(), &p, &r, 0), who);
+    // The damped Newton method starts from weights whose cells are all non-empty.  Extrapolated start
+    // weights (optimize_levels) can miss that for a few cells: the weights are then pulled towards the
+    // Voronoi diagram (all weights equal: every cell of distinct points is non-empty) by halving.
+    for(int attempt = 0;; ++attempt) {
+        const int rc = b200vor_otm_newton(ctx_, nu_level.empty() ? nullptr : nu_level.data(), weights_.data(), &p, &r, 0);
+        if(rc == B200VOR_OK) {
+            break;
+        }
+        const char* msg = b200vor_last_error();
+        if(attempt < 8 && msg && strstr(msg, "an initial cell is empty")) {
+            for(index_t i = 0; i < e; ++i) {
+                weights_[i] *= 0.5;
+            }
+            continue;
+        }
+        check(rc, who);
+    }
     converged_ = r.converged != 0;
     newton_iters_ = r.newton_iters;
 }
@@ -741,6 +758,58 @@ void OptimalTransportMap3d::optimize(index_t max_iterations) {
     measure_.resize(n);
     mg_.resize(3 * size_t(n));
     check(b200vor_get_cells(ctx_, measure_.data(), mg_.data(), nullptr, 0), "OptimalTransportMap3d::optimize (get_cells)");
+}
+
+// value at q of the least-squares plane through (p_j, w_j), j in row[0..k): normal equations in the
+// frame of q (4 unknowns: value at q and gradient), Gaussian elimination with partial pivoting;
+// a rank-deficient neighbourhood (k < 4, coplanar points) falls back to the nearest weight
+double OptimalTransportMap3d::extrapolate_weight(const double* pts, const double* w, const double* q,
+                                                 const uint32_t* row, uint32_t k) {
+    if(k < 4) {
+        return w[row[0]];
+    }
+    double A[4][5] = {};
+    for(uint32_t t = 0; t < k; ++t) {
+        const double* p = pts + 3 * size_t(row[t]);
+        const double f[4] = {1.0, p[0] - q[0], p[1] - q[1], p[2] - q[2]};
+        for(int r = 0; r < 4; ++r) {
+            for(int c = 0; c < 4; ++c) {
+                A[r][c] += f[r] * f[c];
+            }
+            A[r][4] += f[r] * w[row[t]];
+        }
+    }
+    const double scale = A[1][1] + A[2][2] + A[3][3];
+    for(int c = 0; c < 4; ++c) {
+        int piv = c;
+        for(int r = c + 1; r < 4; ++r) {
+            if(fabs(A[r][c]) > fabs(A[piv][c])) {
+                piv = r;
+            }
+        }
+        if(!(fabs(A[piv][c]) > 1e-10 * (c == 0 ? double(k) : scale))) {
+            return w[row[0]];
+        }
+        for(int j = 0; j < 5; ++j) {
+            std::swap(A[c][j], A[piv][j]);
+        }
+        for(int r = c + 1; r < 4; ++r) {
+            const double m = A[r][c] / A[c][c];
+            for(int j = c; j < 5; ++j) {
+                A[r][j] -= m * A[c][j];
+            }
+        }
+    }
+    // back substitution; only the first unknown (the value at q) is wanted, but it depends on all
+    double x[4];
+    for(int r = 3; r >= 0; --r) {
+        double v = A[r][4];
+        for(int j = r + 1; j < 4; ++j) {
+            v -= A[r][j] * x[j];
+        }
+        x[r] = v / A[r][r];
+    }
+    return x[0];
 }
 
 void OptimalTransportMap3d::optimize_levels(const std::vector<index_t>& levels, index_t max_iterations) {
@@ -767,20 +836,25 @@ void OptimalTransportMap3d::optimize_levels(const std::vector<index_t>& levels, 
     for(size_t l = 0; l + 1 < levels.size(); ++l) {
         const index_t b = levels[l], e = levels[l + 1];
         if(b != 0) {
-            // the context still holds the points [0, b) of the level below: every new point takes
-            // the weight of its nearest solved point.  The by-point query is a box query: on a
-            // periodic cube it runs on the cube without the wrap (a start value, not a result).
+            // the context still holds the points [0, b) of the level below: one batched by-point kNN
+            // query on the device.  It is a box query: on a periodic cube it runs on the cube without
+            // the wrap (the rows feed a start value, not a result).
             if(period_ > 0.0) {
                 const double cube[6] = {0.0, 0.0, 0.0, period_, period_, period_};
                 check(b200vor_set_domain_box(ctx_, cube), who);
             }
-            nearest.resize(e - b);
-            check(b200vor_knn_points(ctx_, e - b, points_.data() + 3 * size_t(b), 1, nearest.data(), nullptr, 0), who);
+            // a LINEAR fit of the solved weights over the k nearest solved points, evaluated at the new
+            // point: a piecewise-constant start (nearest weight alone) jumps by |grad w| x (coarse spacing)
+            // between neighbouring new points, more than their squared distance, and empties cells
+            const uint32_t k = std::min<index_t>(b, 12);
+            nearest.resize(size_t(e - b) * k);
+            check(b200vor_knn_points(ctx_, e - b, points_.data() + 3 * size_t(b), k, nearest.data(), nullptr, 0), who);
             if(period_ > 0.0) {
                 check(b200vor_set_domain_periodic(ctx_, period_), who);
             }
             for(index_t i = b; i < e; ++i) {
-                weights_[i] = weights_[nearest[i - b]];
+                const uint32_t* row = nearest.data() + size_t(i - b) * k;
+                weights_[i] = extrapolate_weight(points_.data(), weights_.data(), points_.data() + 3 * size_t(i), row, k);
             }
         }
         solve_prefix(e, max_iterations, who);

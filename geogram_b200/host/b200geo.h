@@ -248,9 +248,15 @@ public:
        filled by the reference's sampling (points in BRIO order: every prefix [0, e_l) is a uniform
        sub-sample).  Level l solves the transport problem of the points [0, e_l) alone (target
        masses rescaled to the measure of the domain); the points that enter at the next level
-       start from the weight of their nearest solved point (one batched by-point kNN query on
-       the device), so that the finest level starts next to its solution. */
+       start from a linear least-squares fit of the solved weights over their 12 nearest solved
+       points (one batched by-point kNN query on the device), so that the finest level starts
+       next to its solution.  A start that still leaves a cell empty is pulled towards the
+       Voronoi diagram (weights halved) until every cell is non-empty (KMT hypothesis). */
     void optimize_levels(const std::vector<index_t>& levels, index_t max_iterations);
+    /* value at q of the least-squares plane through (pts[row[j]], w[row[j]]), j < k (nearest weight
+       when the neighbourhood is rank deficient); pure host code */
+    static double extrapolate_weight(const double* pts, const double* w, const double* q,
+                                     const uint32_t* row, uint32_t k);
     /* Newton iterations of every level of the last optimize_levels call */
     const std::vector<index_t>& level_newton_iterations() const { return level_iters_; }
     index_t nb_points() const { return index_t(weights_.size()); }

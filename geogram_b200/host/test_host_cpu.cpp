@@ -53,6 +53,31 @@ int main() {
     std::vector<global_index_t> none;
     ConvexCellBatch::tet_adjacency(none, adj);
     EXPECT(adj.empty());
+    // ---- OptimalTransportMap3d::extrapolate_weight: a linear weight field is reproduced exactly,
+    //      a coplanar neighbourhood falls back to the nearest weight
+    {
+        std::vector<double> pts, w;
+        std::vector<uint32_t> row;
+        unsigned s = 12345u;
+        for(int i = 0; i < 12; ++i) {
+            double c[3];
+            for(int d = 0; d < 3; ++d) {
+                s = s * 1664525u + 1013904223u;
+                c[d] = double(s >> 8) / double(1u << 24);
+                pts.push_back(c[d]);
+            }
+            w.push_back(0.3 - 1.5 * c[0] + 0.25 * c[1] + 2.0 * c[2]);
+            row.push_back(uint32_t(i));
+        }
+        const double q[3] = {0.4, 0.6, 0.1};
+        const double v = OptimalTransportMap3d::extrapolate_weight(pts.data(), w.data(), q, row.data(), 12);
+        EXPECT(fabs(v - (0.3 - 1.5 * q[0] + 0.25 * q[1] + 2.0 * q[2])) < 1e-10);
+        for(int i = 0; i < 12; ++i) {
+            pts[3 * i + 2] = 0.5;      // all neighbours in one plane
+        }
+        EXPECT(OptimalTransportMap3d::extrapolate_weight(pts.data(), w.data(), q, row.data(), 12) == w[0]);
+        EXPECT(OptimalTransportMap3d::extrapolate_weight(pts.data(), w.data(), q, row.data(), 3) == w[0]);
+    }
     printf(fails ? "host cpu test: %d FAILURES\n" : "host cpu test: ok\n", fails);
     return fails ? 1 : 0;
 }
