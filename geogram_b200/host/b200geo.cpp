@@ -723,16 +723,18 @@ void OptimalTransportMap3d::solve_prefix(index_t e, index_t max_iterations, cons
     p.max_newton = max_iterations;
     p.epsilon = epsilon_;
     b200vor_otm_result r;
-    // The damped Newton method starts from weights whose cells are all non-empty.  Extrapolated start
-    // weights (optimize_levels) can miss that for a few cells: the weights are then pulled towards the
-    // Voronoi diagram (all weights equal: every cell of distinct points is non-empty) by halving.
+    // The damped Newton method starts from weights whose cells are all non-empty and certified.
+    // Extrapolated start weights (optimize_levels) can miss that for a few cells: the weights are then
+    // pulled towards the Voronoi diagram (all weights equal: every cell of distinct points is
+    // non-empty) by halving.
     for(int attempt = 0;; ++attempt) {
         const int rc = b200vor_otm_newton(ctx_, nu_level.empty() ? nullptr : nu_level.data(), weights_.data(), &p, &r, 0);
         if(rc == B200VOR_OK) {
             break;
         }
         const char* msg = b200vor_last_error();
-        if(attempt < 8 && msg && strstr(msg, "an initial cell is empty")) {
+        if(attempt < 8 && msg && (strstr(msg, "an initial cell is empty") ||
+                                  strstr(msg, "of the start weights are flagged"))) {
             for(index_t i = 0; i < e; ++i) {
                 weights_[i] *= 0.5;
             }
@@ -809,7 +811,14 @@ double OptimalTransportMap3d::extrapolate_weight(const double* pts, const double
         }
         x[r] = v / A[r][r];
     }
-    return x[0];
+    // no overshoot: outside the hull of its neighbours (new points next to the domain boundary) the
+    // fit EXTRApolates; the start weight stays within the range of the weights it was fitted to
+    double lo = w[row[0]], hi = w[row[0]];
+    for(uint32_t t = 1; t < k; ++t) {
+        lo = std::min(lo, w[row[t]]);
+        hi = std::max(hi, w[row[t]]);
+    }
+    return std::min(std::max(x[0], lo), hi);
 }
 
 void OptimalTransportMap3d::optimize_levels(const std::vector<index_t>& levels, index_t max_iterations) {
@@ -857,7 +866,12 @@ void OptimalTransportMap3d::optimize_levels(const std::vector<index_t>& levels, 
                 weights_[i] = extrapolate_weight(points_.data(), weights_.data(), points_.data() + 3 * size_t(i), row, k);
             }
         }
-        solve_prefix(e, max_iterations, who);
+        try {
+            solve_prefix(e, max_iterations, who);
+        } catch(const std::runtime_error& err) {
+            throw std::runtime_error(std::string(err.what()) + " [level " + std::to_string(l) + ": points 0.." +
+                                     std::to_string(e) + "]");
+        }
         level_iters_.push_back(newton_iters_);
     }
     measure_.resize(n);
