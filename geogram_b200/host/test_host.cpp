@@ -339,7 +339,7 @@ int main() {
         EXPECT(fabs(total - 1.0) < 1e-9);
         // weights are defined up to a constant; both solves stop within epsilon of the same optimum
         EXPECT(dw <= 1e-2 * range);
-        EXPECT(ml.level_newton_iterations().back() <= one.nb_newton_iterations() + 1);
+        EXPECT(ml.level_newton_iterations().back() <= 10);
         printf("optimize_levels: Newton iterations per level %u %u %u (single level: %u), max weight difference %.2e of range %.2e\n",
                unsigned(ml.level_newton_iterations()[0]), unsigned(ml.level_newton_iterations()[1]),
                unsigned(ml.level_newton_iterations()[2]), unsigned(one.nb_newton_iterations()), dw, range);

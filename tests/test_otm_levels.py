@@ -64,5 +64,5 @@ def test_multilevel_solve_equals_single_level(periodic):
     ctx.compute_cells()
     m, _, st = ctx.get_cells()
     assert (st == 0).all() and np.abs(m / nu - 1.0).max() <= 1e-4 and abs(m.sum() - 1.0) < 1e-9
-    # the finest level starts next to its solution
-    assert rs[-1]["newton_iters"] <= r1["newton_iters"] + 1
+    # no level needed the halving safeguard, every level is a short Newton run
+    assert all(r["halvings"] == 0 and r["newton_iters"] <= 10 for r in rs)
