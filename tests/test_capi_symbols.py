@@ -68,3 +68,30 @@ def test_sass_is_sm100a():
     out = subprocess.check_output(["cuobjdump", "-lelf", capi.LIB_PATH]).decode()
     assert "sm_100a" in out
     assert "sm_90" not in out and "sm_80" not in out
+
+
+def test_ctypes_structs_match_the_header(tmp_path):
+    """The ctypes mirrors in geogram_b200/capi.py have the size and the field offsets the C compiler gives
+    the structs of include/b200vor.h (an ABI drift would corrupt results silently)."""
+    from geogram_b200 import capi
+    pairs = [("b200vor_cell_params", capi.CellParams), ("b200vor_stats", capi.Stats),
+             ("b200vor_otm_params", capi.OtmParams), ("b200vor_otm_result", capi.OtmResult),
+             ("b200vor_peaks", capi.Peaks), ("b200vor_slab_stats", capi.SlabStats)]
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "b200vor.h"', 'int main(void) {']
+    for cname, cls in pairs:
+        lines.append('printf("%s %%zu", sizeof(%s));' % (cname, cname))
+        for fname, _ in cls._fields_:
+            lines.append('printf(" %%zu", offsetof(%s, %s));' % (cname, fname))
+        lines.append('printf("\\n");')
+    lines += ['return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    out = subprocess.check_output([str(exe)]).decode().split("\n")
+    for (cname, cls), line in zip(pairs, out):
+        f = line.split()
+        assert f[0] == cname
+        assert int(f[1]) == ctypes.sizeof(cls), cname
+        for (fname, _), off in zip(cls._fields_, f[2:]):
+            assert int(off) == getattr(cls, fname).offset, (cname, fname)
