@@ -842,6 +842,7 @@ void OptimalTransportMap3d::optimize_levels(const std::vector<index_t>& levels, 
     }
     level_iters_.clear();
     std::vector<uint32_t> nearest;
+    std::vector<double> solved;
     for(size_t l = 0; l + 1 < levels.size(); ++l) {
         const index_t b = levels[l], e = levels[l + 1];
         if(b != 0) {
@@ -852,18 +853,21 @@ void OptimalTransportMap3d::optimize_levels(const std::vector<index_t>& levels, 
                 const double cube[6] = {0.0, 0.0, 0.0, period_, period_, period_};
                 check(b200vor_set_domain_box(ctx_, cube), who);
             }
-            // a LINEAR fit of the solved weights over the k nearest solved points, evaluated at the new
-            // point: a piecewise-constant start (nearest weight alone) jumps by |grad w| x (coarse spacing)
-            // between neighbouring new points, more than their squared distance, and empties cells
-            const uint32_t k = std::min<index_t>(b, 12);
-            nearest.resize(size_t(e - b) * k);
-            check(b200vor_knn_points(ctx_, e - b, points_.data() + 3 * size_t(b), k, nearest.data(), nullptr, 0), who);
+            // a LINEAR fit of the solved weights over the k nearest solved points, evaluated at EVERY point
+            // of the new level, the solved ones included: what carries over between levels is the smooth
+            // part of the potential.  (A nearest-weight copy jumps by |grad w| x (coarse spacing) between
+            // neighbouring new points; the per-point part of the solved weights compensates the cell
+            // irregularities of one level's point set, order (coarse spacing)^2: both empty cells.)
+            const uint32_t k = std::min<index_t>(b, 24);
+            nearest.resize(size_t(e) * k);
+            check(b200vor_knn_points(ctx_, e, points_.data(), k, nearest.data(), nullptr, 0), who);
             if(period_ > 0.0) {
                 check(b200vor_set_domain_periodic(ctx_, period_), who);
             }
-            for(index_t i = b; i < e; ++i) {
-                const uint32_t* row = nearest.data() + size_t(i - b) * k;
-                weights_[i] = extrapolate_weight(points_.data(), weights_.data(), points_.data() + 3 * size_t(i), row, k);
+            solved.assign(weights_.begin(), weights_.begin() + b);
+            for(index_t i = 0; i < e; ++i) {
+                const uint32_t* row = nearest.data() + size_t(i) * k;
+                weights_[i] = extrapolate_weight(points_.data(), solved.data(), points_.data() + 3 * size_t(i), row, k);
             }
         }
         try {

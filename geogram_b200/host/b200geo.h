@@ -247,10 +247,9 @@ public:
        src/examples/exploragram/compute_OTM/main.cpp:292-297): `levels` = {0, e_1, ..., nb_points} as
        filled by the reference's sampling (points in BRIO order: every prefix [0, e_l) is a uniform
        sub-sample).  Level l solves the transport problem of the points [0, e_l) alone (target
-       masses rescaled to the measure of the domain); the points that enter at the next level
-       start from a linear least-squares fit of the solved weights over their 12 nearest solved
-       points (one batched by-point kNN query on the device), so that the finest level starts
-       next to its solution.  A start that still leaves a cell empty is pulled towards the
+       masses rescaled to the measure of the domain); every point of the next level starts from
+       a linear least-squares fit of the solved weights over its 24 nearest solved points (one
+       batched by-point kNN query on the device): the smooth part of the potential carries over.  A start that still leaves a cell empty is pulled towards the
        Voronoi diagram (weights halved) until every cell is non-empty (KMT hypothesis). */
     void optimize_levels(const std::vector<index_t>& levels, index_t max_iterations);
     /* value at q of the least-squares plane through (pts[row[j]], w[row[j]]), j < k (nearest weight

@@ -31,7 +31,7 @@ def extrapolate_weights(pts, w, q, rows):
     return out
 
 
-def optimize_levels(ctx, xyz, levels, nu=None, epsilon=0.01, max_newton=0, period=0.0, k_fit=12, log=None):
+def optimize_levels(ctx, xyz, levels, nu=None, epsilon=0.01, max_newton=0, period=0.0, k_fit=24, log=None):
     """ctx: a Context whose domain is set; xyz (n, 3) in BRIO order; levels = [0, e_1, ..., n].
     Returns (w, list of per-level result dicts)."""
     xyz = np.ascontiguousarray(xyz, np.float64)
@@ -45,10 +45,14 @@ def optimize_levels(ctx, xyz, levels, nu=None, epsilon=0.01, max_newton=0, perio
             # the context still holds the points [0, b): one batched by-point kNN query (a box query)
             if period > 0.0:
                 ctx.set_domain_box([0, 0, 0, period, period, period])
-            rows, _ = ctx.knn_points(xyz[b:e], min(b, k_fit))
+            rows, _ = ctx.knn_points(xyz[:e], min(b, k_fit))
             if period > 0.0:
                 ctx.set_domain_periodic(period)
-            w[b:e] = extrapolate_weights(xyz[:b], w[:b], xyz[b:e], rows.astype(np.int64))
+            # ALL points of the new level, the solved ones included, start from the fitted (low-pass)
+            # field: what carries over between levels is the smooth part of the potential; the per-point
+            # part compensates the cell irregularities of ONE level's point set (order h_coarse^2, as large
+            # as the squared spacing of the next level) and empties cells when it is carried along
+            w[:e] = extrapolate_weights(xyz[:b], w[:b].copy(), xyz[:e], rows.astype(np.int64))
         nu_l = None
         if nu is not None:
             nu_l = np.asarray(nu[:e], np.float64) * (np.sum(nu) / np.sum(nu[:e]))
