@@ -892,4 +892,111 @@ vec3 OptimalTransportMap3d::cell_centroid(index_t i) const {
     return r;
 }
 
+// ------------------------------------------------------------------ BRIO order
+uint64_t hilbert_index_3d(uint32_t x, uint32_t y, uint32_t z, int bits) {
+    uint32_t X[3] = {x, y, z};
+    // axes -> transpose (J. Skilling, "Programming the Hilbert curve", 2004)
+    for(uint32_t Q = 1u << (bits - 1); Q > 1; Q >>= 1) {
+        const uint32_t P = Q - 1;
+        for(int i = 0; i < 3; ++i) {
+            if(X[i] & Q) {
+                X[0] ^= P;
+            } else {
+                const uint32_t t = (X[0] ^ X[i]) & P;
+                X[0] ^= t;
+                X[i] ^= t;
+            }
+        }
+    }
+    X[1] ^= X[0];
+    X[2] ^= X[1];
+    uint32_t t = 0;
+    for(uint32_t Q = 1u << (bits - 1); Q > 1; Q >>= 1) {
+        if(X[2] & Q) {
+            t ^= Q - 1;
+        }
+    }
+    uint64_t key = 0;
+    for(int i = 0; i < 3; ++i) {
+        X[i] ^= t;
+    }
+    for(int b = 0; b < bits; ++b) {
+        for(int i = 0; i < 3; ++i) {
+            key |= uint64_t((X[i] >> b) & 1u) << (3 * b + (2 - i));
+        }
+    }
+    return key;
+}
+
+void compute_BRIO_order(index_t nb_vertices, const double* vertices, std::vector<index_t>& sorted_indices,
+                        index_t stride, index_t threshold, double ratio, std::vector<index_t>* levels,
+                        uint64_t seed) {
+    const index_t n = nb_vertices;
+    sorted_indices.resize(n);
+    for(index_t i = 0; i < n; ++i) {
+        sorted_indices[i] = i;
+    }
+    if(levels) {
+        levels->clear();
+        levels->push_back(0);
+    }
+    if(n == 0) {
+        return;
+    }
+    // Fisher-Yates with a 64-bit LCG (the reference uses GEO::random_shuffle: another stream of numbers)
+    uint64_t state = seed * 6364136223846793005ull + 1442695040888963407ull;
+    for(index_t i = n - 1; i > 0; --i) {
+        state = state * 6364136223846793005ull + 1442695040888963407ull;
+        const index_t j = index_t((state >> 33) % uint64_t(i + 1));
+        std::swap(sorted_indices[i], sorted_indices[j]);
+    }
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for(index_t i = 0; i < n; ++i) {
+        for(int d = 0; d < 3; ++d) {
+            lo[d] = std::min(lo[d], vertices[size_t(i) * stride + d]);
+            hi[d] = std::max(hi[d], vertices[size_t(i) * stride + d]);
+        }
+    }
+    const int bits = 16;
+    double scale[3];
+    for(int d = 0; d < 3; ++d) {
+        scale[d] = hi[d] > lo[d] ? double(1u << bits) / (hi[d] - lo[d]) : 0.0;
+    }
+    // the nested intervals from the outside in (mesh_reorder.cpp:1126-1136): [m, e) is sorted, [b, m) recursed
+    std::vector<std::pair<index_t, index_t> > bounds;
+    index_t e = n;
+    for(;;) {
+        index_t m = 0;
+        if(e > threshold) {
+            m = index_t(double(e) * ratio);
+        }
+        bounds.push_back(std::make_pair(m, e));
+        if(m == 0) {
+            break;
+        }
+        e = m;
+    }
+    std::vector<std::pair<uint64_t, index_t> > keyed;
+    for(size_t l = bounds.size(); l-- > 0;) {
+        const index_t m = bounds[l].first, end = bounds[l].second;
+        keyed.resize(end - m);
+        for(index_t i = m; i < end; ++i) {
+            const double* p = vertices + size_t(sorted_indices[i]) * stride;
+            uint32_t q[3];
+            for(int d = 0; d < 3; ++d) {
+                const double v = (p[d] - lo[d]) * scale[d];
+                q[d] = uint32_t(std::min(std::max(v, 0.0), double((1u << bits) - 1)));
+            }
+            keyed[i - m] = std::make_pair(hilbert_index_3d(q[0], q[1], q[2], bits), sorted_indices[i]);
+        }
+        std::sort(keyed.begin(), keyed.end());
+        for(index_t i = m; i < end; ++i) {
+            sorted_indices[i] = keyed[i - m].second;
+        }
+        if(levels) {
+            levels->push_back(end);
+        }
+    }
+}
+
 }  // namespace B200GEO

@@ -279,6 +279,18 @@ private:
     void solve_prefix(index_t e, index_t max_iterations, const char* who);
 };
 
+/* BRIO order and its levels (GEO::compute_BRIO_order, mesh/mesh_reorder.cpp:1287-1315; dimension 3):
+   random shuffle, then recursively the first `ratio` of every interval longer than `threshold`; the rest of
+   the interval is sorted along the 3-D Hilbert curve of a 2^16 lattice over the bounding box (the reference
+   sorts by recursive median splits: same role, not the same permutation); `levels` (optional) = {0, end of
+   every interval} -- identical to the reference's for the same sizes.  Feeds
+   OptimalTransportMap3d::optimize_levels.  Pure host code. */
+void compute_BRIO_order(index_t nb_vertices, const double* vertices, std::vector<index_t>& sorted_indices,
+                        index_t stride = 3, index_t threshold = 300, double ratio = 0.125,
+                        std::vector<index_t>* levels = nullptr, uint64_t seed = 0);
+/* index of the lattice point (x, y, z), each below 2^bits, on the 3-D Hilbert curve (Skilling's transpose form) */
+uint64_t hilbert_index_3d(uint32_t x, uint32_t y, uint32_t z, int bits);
+
 }  // namespace B200GEO
 
 #endif

@@ -3,6 +3,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "b200geo.h"
@@ -77,6 +78,57 @@ int main() {
         }
         EXPECT(OptimalTransportMap3d::extrapolate_weight(pts.data(), w.data(), q, row.data(), 12) == w[0]);
         EXPECT(OptimalTransportMap3d::extrapolate_weight(pts.data(), w.data(), q, row.data(), 3) == w[0]);
+    }
+    // ---- compute_BRIO_order: levels of the unmodified reference (tests/golden/brio_reference.npz), Hilbert walk
+    {
+        const int b = 3;
+        std::vector<uint64_t> seen(size_t(1) << (3 * b), 0);
+        std::vector<int> at(3 * (size_t(1) << (3 * b)));
+        for(uint32_t x = 0; x < (1u << b); ++x) {
+            for(uint32_t y = 0; y < (1u << b); ++y) {
+                for(uint32_t z = 0; z < (1u << b); ++z) {
+                    const uint64_t h = hilbert_index_3d(x, y, z, b);
+                    EXPECT(h < seen.size() && seen[h] == 0);
+                    seen[h] = 1;
+                    at[3 * h] = int(x);
+                    at[3 * h + 1] = int(y);
+                    at[3 * h + 2] = int(z);
+                }
+            }
+        }
+        for(size_t h = 1; h < seen.size(); ++h) {     // consecutive curve positions are lattice neighbours
+            EXPECT(abs(at[3 * h] - at[3 * h - 3]) + abs(at[3 * h + 1] - at[3 * h - 2]) + abs(at[3 * h + 2] - at[3 * h - 1]) == 1);
+        }
+        const index_t n = 20000;
+        std::vector<double> pts(3 * size_t(n));
+        unsigned s = 99u;
+        for(size_t i = 0; i < pts.size(); ++i) {
+            s = s * 1664525u + 1013904223u;
+            pts[i] = double(s >> 8) / double(1u << 24);
+        }
+        std::vector<index_t> order, levels;
+        compute_BRIO_order(n, pts.data(), order, 3, 300, 0.125, &levels);
+        const index_t ref[5] = {0, 39, 312, 2500, 20000};
+        EXPECT(levels.size() == 5);
+        for(size_t l = 0; l < 5 && l < levels.size(); ++l) {
+            EXPECT(levels[l] == ref[l]);
+        }
+        std::vector<index_t> sorted(order);
+        std::sort(sorted.begin(), sorted.end());
+        for(index_t i = 0; i < n; ++i) {
+            EXPECT(sorted[i] == i);
+        }
+        // the last interval is local: mean step far below the mean distance of random pairs (0.66)
+        double step = 0.0;
+        for(index_t i = 2501; i < n; ++i) {
+            double d2 = 0.0;
+            for(int d = 0; d < 3; ++d) {
+                const double t = pts[3 * size_t(order[i]) + d] - pts[3 * size_t(order[i - 1]) + d];
+                d2 += t * t;
+            }
+            step += sqrt(d2);
+        }
+        EXPECT(step / double(n - 2501) < 0.1);
     }
     printf(fails ? "host cpu test: %d FAILURES\n" : "host cpu test: ok\n", fails);
     return fails ? 1 : 0;

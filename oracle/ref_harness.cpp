@@ -34,6 +34,7 @@
 #include <geogram/delaunay/periodic_delaunay_3d.h>
 #include <geogram/points/nn_search.h>
 #include <geogram/voronoi/convex_cell.h>
+#include <geogram/mesh/mesh_reorder.h>
 
 #include <algorithm>
 #include <atomic>
@@ -352,6 +353,22 @@ uint32_t georef_delaunay_tets(uint32_t n, const double* xyz, uint32_t* tets, uin
         ++count;
     }
     return count;
+}
+
+/* BRIO order and levels of the unmodified reference (compute_BRIO_order, mesh/mesh_reorder.cpp:1287-1315):
+ * order[n], levels[cap]; returns the number of levels written (levels[0] = 0 ... = n) */
+uint32_t georef_brio_order(uint32_t n, const double* xyz, uint32_t threshold, double ratio,
+                           uint32_t* order, uint32_t* levels, uint32_t cap) {
+    georef_init(0);
+    GEO::vector<GEO::index_t> sorted, lv;
+    GEO::compute_BRIO_order(n, xyz, sorted, 3, 3, threshold, ratio, &lv);
+    for(uint32_t i = 0; i < n; ++i) {
+        order[i] = uint32_t(sorted[i]);
+    }
+    for(uint32_t l = 0; l < lv.size() && l < cap; ++l) {
+        levels[l] = uint32_t(lv[l]);
+    }
+    return uint32_t(lv.size());
 }
 
 /*

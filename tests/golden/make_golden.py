@@ -128,8 +128,30 @@ def lattice():
     save_cells("cells_box_lattice_exact_1728.npz", xyz, B, box=box)
 
 
+def brio():
+    """BRIO levels of the unmodified reference (compute_BRIO_order, mesh_reorder.cpp:1287-1315) for several
+    sizes / thresholds / ratios, and its order on 20 000 seeds (for the statistics of the prefixes and the
+    locality of the last interval, which geogram_b200/ordering.py must match in kind)."""
+    R = oracles.Reference()
+    cases, out = [(20000, 300, 0.125), (4000, 300, 0.125), (301, 300, 0.125), (299, 300, 0.125),
+                  (123457, 64, 0.25), (1000000, 300, 0.125)], {}
+    for n, th, r in cases:
+        xyz = oracles.uniform_seeds(n, 777)
+        order, levels = R.brio_order(xyz, th, r)
+        assert np.array_equal(np.sort(order), np.arange(n))
+        out["levels_%d_%d_%g" % (n, th, r)] = levels
+        if n == 20000:
+            out["xyz_20000"] = xyz
+            out["order_20000"] = order
+    out["cases"] = np.array(cases)
+    np.savez_compressed(os.path.join(HERE, "brio_reference.npz"), **out)
+    print("brio_reference.npz", {k: v.tolist() for k, v in out.items() if k.startswith("levels")})
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "lattice":
+    if len(sys.argv) > 1 and sys.argv[1] == "brio":
+        brio()
+    elif len(sys.argv) > 1 and sys.argv[1] == "lattice":
         lattice()
     elif len(sys.argv) > 1 and sys.argv[1] == "cvt":
         cvt_energy()

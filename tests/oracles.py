@@ -190,6 +190,18 @@ class Reference(object):
         assert cnt <= cap
         return tets[:cnt]
 
+    def brio_order(self, xyz, threshold=300, ratio=0.125):
+        """(order, levels) of the reference's compute_BRIO_order (mesh_reorder.cpp:1287-1315)."""
+        xyz = np.ascontiguousarray(xyz, np.float64)
+        n = xyz.shape[0]
+        order = np.zeros(n, np.uint32)
+        levels = np.zeros(64, np.uint32)
+        self.lib.georef_brio_order.restype = ctypes.c_uint32
+        cnt = self.lib.georef_brio_order(ctypes.c_uint32(n), _p(xyz, _cd), ctypes.c_uint32(threshold),
+                                         ctypes.c_double(ratio), _p(order, _cu), _p(levels, _cu), ctypes.c_uint32(64))
+        assert cnt <= 64
+        return order, levels[:cnt].copy()
+
     def cells_knn(self, xyz, w=None, box=UNIT_BOX, k0=20, kcap=1000, exact=True,
                   fcap=64, areas=False, domain=None):
         """Oracle B.  domain: optional (k,4) planes of a convex domain, clipped by the reference's own

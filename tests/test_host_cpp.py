@@ -42,6 +42,7 @@ def test_host_library_exports_the_mirrored_interfaces():
         "B200GEO::OptimalTransportMap3d::set_points(unsigned int, double const*)",
         "B200GEO::OptimalTransportMap3d::optimize(unsigned int)",
         "B200GEO::OptimalTransportMap3d::optimize_levels(",
+        "B200GEO::compute_BRIO_order(",
     ]:
         assert sym in out, sym
     # the host library reaches the device only through the C ABI
