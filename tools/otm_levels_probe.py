@@ -11,6 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from geogram_b200 import Context  # noqa: E402
 from geogram_b200.otm import optimize_levels  # noqa: E402
+from geogram_b200.ordering import brio_order  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 4000
 ratio = float(sys.argv[2]) if len(sys.argv) > 2 else 0.125
@@ -23,10 +24,9 @@ xyz = ctx.lloyd(5)                     # a sampling of the unit cube, in random 
 amp = float(sys.argv[3]) if len(sys.argv) > 3 else 0.1
 nu = 1.0 + amp * np.sin(2 * np.pi * xyz[:, 0])
 nu /= nu.sum()
-levels = [n]
-while levels[0] * ratio >= 200:
-    levels.insert(0, int(levels[0] * ratio))
-levels.insert(0, 0)
+order, levels = brio_order(xyz, threshold=300, ratio=ratio)     # GEO::compute_BRIO_order's intervals
+xyz = np.ascontiguousarray(xyz[order])
+nu = nu[order]
 ctx.set_points(xyz)
 t0 = time.perf_counter()
 w1, r1 = ctx.otm_newton(nu=nu, epsilon=1e-3)
