@@ -183,3 +183,23 @@ def test_affine_weights_equal_a_translation_of_the_sites(port):
     assert np.array_equal(A.nfaces[ok], B.nfaces[ok])
     for i in np.nonzero(ok)[0]:
         assert sorted(A.faces(i)) == sorted(B.faces(i))
+
+
+def test_quadratic_weights_equal_a_homothety_of_the_diagram(port):
+    """(p_j, u_j + c |p_j|^2) in x-space is the (1 - c)-scaled image of (p_j, u_j / (1 - c)): with x = (1 - c) x'
+    the |x|^2-free part -2 x.p_j + (1 - c) |p_j|^2 - u_j is (1 - c) times -2 x'.p_j + |p_j|^2 - u_j / (1 - c)
+    (DESIGN.md section 8 item 1b)."""
+    rng = np.random.default_rng(6)
+    n = 3000
+    xyz = 0.2 + 0.6 * rng.random((n, 3))
+    u = 0.0005 * rng.random(n)
+    c = 0.02
+    s = 1.0 - c
+    A = port.cells(xyz, w=u + c * (xyz ** 2).sum(axis=1), periodic=False, kcap=2000)
+    B = port.cells(xyz, w=u / s, periodic=False, kcap=2000, box=oracles.UNIT_BOX / s)
+    ok = (A.flags == 0) & (B.flags == 0)
+    assert ok.sum() > 0.5 * n
+    assert np.abs(A.m - s ** 3 * B.m)[ok].max() <= 1e-12 * A.m.max()
+    assert np.abs(A.mg - s ** 4 * B.mg)[ok].max() <= 1e-12 * np.abs(A.mg).max()
+    for i in np.nonzero(ok)[0]:
+        assert sorted(A.faces(i)) == sorted(B.faces(i))
